@@ -1,0 +1,75 @@
+"""ctypes loader for libimagharmony_sm100.so (the C ABI declared in include/ih_api.h).
+
+The product path has no CPU / PyTorch fallback: if the shared library is missing or a symbol is absent this module
+raises, and every op raises ``IHError`` on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libimagharmony_sm100.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+
+class IHError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); must list every symbol of include/ih_api.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "ih_last_error": (c_char_p, []),
+    "ih_version": (c_int, []),
+    "ih_launch_count": (c_longlong, []),
+    "ih_launch_count_reset": (None, []),
+    "ih_gemm_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p,
+                            c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ih_conv2d_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ih_attention_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                 c_longlong, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ih_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_float, c_int, c_void_p]),
+    "ih_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "ih_linear_small_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                    c_int, c_int, c_int, c_void_p]),
+    "ih_sinusoid_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "ih_upsample2x_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ih_concat_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
+    "ih_conv_in_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ih_conv_out_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ih_euler_cfg_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_longlong, c_int,
+                                  c_void_p]),
+    "ih_scale_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once). Raises IHError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IHError(
+            f"{LIB_NAME} not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C imagharmony_b200/csrc` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise IHError(f"{LIB_NAME} does not export {name}") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ih_last_error()
+        raise IHError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")

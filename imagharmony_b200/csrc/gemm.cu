@@ -1,0 +1,457 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] * W[N,K]^T )           fp16 in, fp32 accumulate in TMEM, fp16 out
+//
+// One CTA computes one 128 x BN output tile. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single
+// thread tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> global). Operands are staged by TMA into
+// 128B-swizzled shared memory (64 fp16 = one 128 B row per K-block), STAGES-deep mbarrier ring.
+//
+// Convolution is the same kernel ("im2col-free"): the activation is NHWC, the A tile of tap (dy,dx) is a 4-D TMA box
+// {64 channels, bw, bh, 1} at spatial offset (dx-1, dy-1) with out-of-bounds zero fill providing the padding; the
+// weight is [Cout, taps*Cin] tap-major. Stride-2 convolutions read four parity-subsampled views of the input.
+//
+// Replaces (reference call sites): nn.Linear in attention_processor.py:292-320,396-453 (to_q/to_k/to_v/to_out,
+// to_k_ip/to_v_ip) and, in the diffusers UNet the reference drives at custom_pipelines.py:338-345, every Linear
+// (proj_in/out, FF GEGLU) and Conv2d.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ih_api.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ih {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int GEMM_THREADS = 192;
+
+struct alignas(64) TmapSet4 {
+  CUtensorMap m[4];
+};
+
+struct GemmParams {
+  int M, N;     // logical output rows / cols (GEGLU: N = number of gated outputs)
+  int num_kb;   // K blocks of 64 (taps * cin_kb for conv)
+  int mode;     // 0 = plain GEMM, 1 = conv (4-D A maps)
+  int cin_kb;   // conv: K blocks per tap
+  int Ho, Wo;   // conv: output spatial size
+  int bw, bh;   // conv: spatial tile (bw*bh == 128)
+  int tiles_x, tiles_y;
+  signed char tap_map[12], tap_ox[12], tap_oy[12];
+  int gate_row_off;  // GEGLU: row offset of the gate half inside W
+  const __half* bias;
+  const __half* rowbias;
+  int rows_per_group;
+  long long ld_rowbias;
+  const __half* residual;
+  long long ldr;
+  __half* out;
+  long long ldo;
+  int act;  // 0 none, 1 SiLU (applied after bias, before residual)
+};
+
+template <int BN, int STAGES, bool GEGLU>
+struct GemmSmem {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES, bool GEGLU>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_constant__ TmapSet4 amaps,
+                                                                 const __grid_constant__ CUtensorMap bmap,
+                                                                 const GemmParams p) {
+  using S = GemmSmem<BN, STAGES, GEGLU>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y;
+  constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
+  const int n0 = n_tile * BN_OUT;
+
+  // tile origin
+  int m0 = m_tile * BM;
+  int img = 0, x0 = 0, y0 = 0;
+  if (p.mode == 1) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    img = m_tile / per_img;
+    const int t = m_tile - img * per_img;
+    y0 = (t / p.tiles_x) * p.bh;
+    x0 = (t % p.tiles_x) * p.bw;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amaps.m[0]);
+    tma_prefetch_desc(&bmap);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256)>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+        uint8_t* sB = sA + A_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        if (p.mode == 0) {
+          tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
+        } else {
+          const int tap = kb / p.cin_kb;
+          const int ckb = kb - tap * p.cin_kb;
+          tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
+                      y0 + p.tap_oy[tap], img);
+        }
+        if (GEGLU) {
+          tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+          tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
+        } else {
+          tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint64_t a_desc = umma_desc_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    bool row_ok;
+    long long orow;
+    if (p.mode == 0) {
+      orow = (long long)m0 + r;
+      row_ok = orow < p.M;
+    } else {
+      const int hh = r / p.bw, ww = r - hh * p.bw;
+      const int y = y0 + hh, x = x0 + ww;
+      row_ok = (y < p.Ho) && (x < p.Wo) && (img * (long long)p.Ho * p.Wo < p.M);
+      orow = ((long long)img * p.Ho + y) * p.Wo + x;
+    }
+    const __half* rb = nullptr;
+    if (p.rowbias && row_ok) rb = p.rowbias + (orow / p.rows_per_group) * p.ld_rowbias;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+#pragma unroll 1
+    for (int c = 0; c < BN_OUT / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + c * 32, v);
+      uint32_t g[32];
+      if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, g);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = col0 + j * 8;
+          if (col < p.N) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
+            if (p.bias) {
+              const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + col);
+              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_half2(bw[e]);
+                x[2 * e] += f.x;
+                x[2 * e + 1] += f.y;
+              }
+            }
+            if (GEGLU) {
+              float gt[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j * 8 + e]);
+              if (p.bias) {
+                const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col);
+                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_half2(bw[e]);
+                  gt[2 * e] += f.x;
+                  gt[2 * e + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
+            }
+            if (rb) {
+              const uint4 b4 = *reinterpret_cast<const uint4*>(rb + col);
+              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_half2(bw[e]);
+                x[2 * e] += f.x;
+                x[2 * e + 1] += f.y;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
+            }
+            if (p.residual) {
+              const uint4 b4 = *reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_half2(bw[e]);
+                x[2 * e] += f.x;
+                x[2 * e + 1] += f.y;
+              }
+            }
+            uint4 o;
+            o.x = pack_half2(x[0], x[1]);
+            o.y = pack_half2(x[2], x[3]);
+            o.z = pack_half2(x[4], x[5]);
+            o.w = pack_half2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<(BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256)>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool GEGLU>
+static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, const GemmParams& p, int m_tiles,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES, GEGLU>;
+  static bool configured = false;
+  auto kern = gemm_f16_kernel<BN, STAGES, GEGLU>;
+  if (!configured) {
+    IH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
+  dim3 grid((p.N + BN_OUT - 1) / BN_OUT, m_tiles, 1);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(amaps, bmap, p);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// crude cost model: waves * per-tile time; small BN tiles are shared-memory-bandwidth limited.
+static int pick_bn(long long m_tiles, int N) {
+  const int sms = num_sms();
+  double best = 1e30;
+  int best_bn = 128;
+  const int cands[3] = {256, 128, 64};
+  const double tile_cost[3] = {2.0, 1.0, 0.62};
+  const int occ[3] = {1, 2, 2};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long slots = (long long)sms * occ[i];
+    const long long waves = (tiles + slots - 1) / slots;
+    // two co-resident CTAs share one tensor pipe: a full wave of occ=2 costs occ * tile_cost
+    const double t = (double)waves * tile_cost[i] * occ[i] + 0.15 * waves;
+    if (t < best - 1e-9) {
+      best = t;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long long K, GemmParams& p, int m_tiles,
+                    int geglu, int force_bn, cudaStream_t stream) {
+  int bn = geglu ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
+  CUtensorMap bmap;
+  const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)ldw_rows};
+  const uint64_t bstr[1] = {(uint64_t)K * 2};
+  const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(geglu ? 128 : bn)};
+  int rc = get_tmap_f16(&bmap, w, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+  if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, p, m_tiles, stream);
+  switch (bn) {
+    case 256: return launch_gemm<256, 4, false>(amaps, bmap, p, m_tiles, stream);
+    case 128: return launch_gemm<128, 3, false>(amaps, bmap, p, m_tiles, stream);
+    case 64: return launch_gemm<64, 4, false>(amaps, bmap, p, m_tiles, stream);
+    default: return set_error(IH_ERR_ARG, "unsupported BN %d", bn);
+  }
+}
+
+}  // namespace ih
+
+using namespace ih;
+
+extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
+                           int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
+                           long long ldo, int M, int N, int K, int epilogue, int tile_n, void* stream) {
+  IH_CHECK(a && w && out, IH_ERR_ARG, "ih_gemm_f16: null pointer");
+  IH_CHECK(M > 0 && N > 0 && K > 0, IH_ERR_SHAPE, "ih_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
+  IH_CHECK(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, IH_ERR_ALIGN,
+           "ih_gemm_f16: K, N, lda, ldo must be multiples of 8 (16-byte rows)");
+  const bool geglu = (epilogue & IH_EPI_GEGLU) != 0;
+  IH_CHECK(!geglu || (N % 16 == 0), IH_ERR_SHAPE, "ih_gemm_f16: GEGLU needs even split of N");
+  IH_CHECK(!(residual) || ldr % 8 == 0, IH_ERR_ALIGN, "ih_gemm_f16: ldr must be a multiple of 8");
+  IH_CHECK(!rowbias || (rows_per_group > 0 && ld_rowbias % 8 == 0), IH_ERR_ARG,
+           "ih_gemm_f16: rowbias needs rows_per_group > 0 and ld_rowbias %% 8 == 0");
+
+  TmapSet4 amaps;
+  const uint64_t adims[2] = {(uint64_t)K, (uint64_t)M};
+  const uint64_t astr[1] = {(uint64_t)lda * 2};
+  const uint32_t abox[2] = {(uint32_t)BK, (uint32_t)BM};
+  int rc = get_tmap_f16(&amaps.m[0], a, 2, adims, astr, abox);
+  if (rc) return rc;
+  amaps.m[1] = amaps.m[2] = amaps.m[3] = amaps.m[0];
+
+  GemmParams p{};
+  p.M = M;
+  p.N = geglu ? N / 2 : N;
+  p.num_kb = (K + BK - 1) / BK;
+  p.mode = 0;
+  p.gate_row_off = geglu ? N / 2 : 0;
+  p.bias = (const __half*)bias;
+  p.rowbias = (const __half*)rowbias;
+  p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  p.ld_rowbias = ld_rowbias;
+  p.residual = (const __half*)residual;
+  p.ldr = ldr;
+  p.out = (__half*)out;
+  p.ldo = ldo;
+  p.act = (epilogue & IH_EPI_SILU) ? 1 : 0;
+  const int m_tiles = (M + BM - 1) / BM;
+  return dispatch(amaps, w, N, K, p, m_tiles, geglu, tile_n, (cudaStream_t)stream);
+}
+
+extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias,
+                             long long ld_rowbias, const void* residual, void* out, int B, int Hin, int Win, int Cin,
+                             int Cout, int ksize, int stride, int tile_n, void* stream) {
+  IH_CHECK(x && w && out, IH_ERR_ARG, "ih_conv2d_f16: null pointer");
+  IH_CHECK(ksize == 3, IH_ERR_ARG, "ih_conv2d_f16: ksize must be 3 (1x1 convs are ih_gemm_f16)");
+  IH_CHECK(stride == 1 || stride == 2, IH_ERR_ARG, "ih_conv2d_f16: stride must be 1 or 2");
+  IH_CHECK(Cin % 8 == 0 && Cout % 8 == 0, IH_ERR_ALIGN, "ih_conv2d_f16: channels must be multiples of 8");
+  IH_CHECK(stride == 1 || (Hin % 2 == 0 && Win % 2 == 0), IH_ERR_SHAPE, "ih_conv2d_f16: stride 2 needs even H, W");
+  const int Ho = Hin / stride, Wo = Win / stride;
+
+  // spatial tile: bw x bh = 128 output pixels, minimise padded tiles
+  int best_bw = 128;
+  long long best_tiles = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long long t = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
+    if (best_tiles < 0 || t < best_tiles) {
+      best_tiles = t;
+      best_bw = bw;
+    }
+  }
+  GemmParams p{};
+  p.bw = best_bw;
+  p.bh = 128 / best_bw;
+  p.tiles_x = (Wo + p.bw - 1) / p.bw;
+  p.tiles_y = (Ho + p.bh - 1) / p.bh;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.mode = 1;
+  p.cin_kb = (Cin + BK - 1) / BK;
+  p.num_kb = 9 * p.cin_kb;
+  p.M = B * Ho * Wo;
+  p.N = Cout;
+  p.bias = (const __half*)bias;
+  p.rowbias = (const __half*)rowbias;
+  p.rows_per_group = Ho * Wo;
+  p.ld_rowbias = ld_rowbias;
+  p.residual = (const __half*)residual;
+  p.ldr = Cout;
+  p.out = (__half*)out;
+  p.ldo = Cout;
+
+  TmapSet4 amaps;
+  const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+  if (stride == 1) {
+    const uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    const uint64_t astr[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    int rc = get_tmap_f16(&amaps.m[0], x, 4, adims, astr, abox);
+    if (rc) return rc;
+    amaps.m[1] = amaps.m[2] = amaps.m[3] = amaps.m[0];
+    for (int t = 0; t < 9; ++t) {
+      p.tap_map[t] = 0;
+      p.tap_ox[t] = (signed char)(t % 3 - 1);
+      p.tap_oy[t] = (signed char)(t / 3 - 1);
+    }
+  } else {
+    // input row 2*oy + dy - 1: dy=0 -> odd rows at oy-1, dy=1 -> even rows at oy, dy=2 -> odd rows at oy
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const __half* base = (const __half*)x + ((long long)py * Win + px) * Cin;
+        const uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)Win / 2, (uint64_t)Hin / 2, (uint64_t)B};
+        const uint64_t astr[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        int rc = get_tmap_f16(&amaps.m[py * 2 + px], base, 4, adims, astr, abox);
+        if (rc) return rc;
+      }
+    const int par[3] = {1, 0, 1};
+    const int off[3] = {-1, 0, 0};
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3, dx = t % 3;
+      p.tap_map[t] = (signed char)(par[dy] * 2 + par[dx]);
+      p.tap_ox[t] = (signed char)off[dx];
+      p.tap_oy[t] = (signed char)off[dy];
+    }
+  }
+  const int m_tiles = B * p.tiles_x * p.tiles_y;
+  // weight is [Cout, 9*Cin] tap-major; when Cin is not a multiple of 64 each tap's K range is padded by TMA zero fill
+  IH_CHECK(Cin % BK == 0, IH_ERR_SHAPE, "ih_conv2d_f16: Cin must be a multiple of 64 (got %d)", Cin);
+  return dispatch(amaps, w, Cout, (long long)9 * Cin, p, m_tiles, 0, tile_n, (cudaStream_t)stream);
+}

@@ -1,0 +1,34 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, TMA tensor-map encoding + cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ih {
+
+// error plumbing (thread-local message returned by ih_last_error())
+int set_error(int code, const char* fmt, ...);
+#define IH_CHECK(cond, code, ...)                       \
+  do {                                                  \
+    if (!(cond)) return ::ih::set_error((code), __VA_ARGS__); \
+  } while (0)
+#define IH_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return ::ih::set_error(-100, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+enum { IH_ERR_ARG = -1, IH_ERR_SHAPE = -2, IH_ERR_ALIGN = -3, IH_ERR_TMAP = -4, IH_ERR_CUDA = -100 };
+
+// Encode (or fetch from the process-wide cache) a tiled fp16 tensor map with 128-byte swizzle.
+// dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1].
+// Returns 0 on success.
+int get_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, bool swizzle128 = true);
+
+int num_sms();
+
+// launch counter (all kernels launched by this library since the last reset) -- bench.py's "gpu_launches"
+void count_launch(int n = 1);
+
+}  // namespace ih

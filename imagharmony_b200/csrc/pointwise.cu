@@ -1,0 +1,369 @@
+// Small / bandwidth-bound kernels of the denoise step: small-M linear (time embeddings), sinusoidal embedding,
+// nearest 2x upsample, channel concat, conv_in / conv_out (4-channel ends of the UNet, NCHW <-> NHWC), and the fused
+// CFG-combine + Euler update + next-step input scaling (custom_pipelines.py:332-334,348-357).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/ih_api.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ih {
+
+__device__ __forceinline__ void ld8(const __half* p, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_half2(w[e]);
+    x[2 * e] = f.x;
+    x[2 * e + 1] = f.y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[m, n] = act_out( W[n, :] . act_in(x[m, :]) + b[n] ),  M <= 8.  One warp per output column; W is read once.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SL_MAXM = 8;
+__global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ w,
+                                    const __half* __restrict__ bias, __half* __restrict__ out, long long ldo, int M,
+                                    int N, int K, int act_in, int act_out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[SL_MAXM];
+#pragma unroll
+  for (int m = 0; m < SL_MAXM; ++m) acc[m] = 0.f;
+  const __half* wr = w + (long long)n * K;
+  for (int k = lane * 8; k < K; k += 256) {
+    float wv[8];
+    ld8(wr + k, wv);
+#pragma unroll
+    for (int m = 0; m < SL_MAXM; ++m) {
+      if (m < M) {
+        float xv[8];
+        ld8(x + m * ldx + k, xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float xe = xv[e];
+          if (act_in == 1) xe = __half2float(__float2half_rn(silu_f(xe)));  // SiLU output is fp16 in the reference
+          acc[m] += wv[e] * xe;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SL_MAXM; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    const float b = bias ? __half2float(bias[n]) : 0.f;
+    for (int m = 0; m < M; ++m) {
+      float y = __half2float(__float2half_rn(acc[m] + b));  // nn.Linear output is fp16 before the activation
+      if (act_out == 1) y = silu_f(y);
+      out[m * ldo + n] = __float2half_rn(y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sinusoid(t, dim) = [cos(t f_j), sin(t f_j)], f_j = exp(-ln(10000) j / half)   (flip_sin_to_cos=True, shift 0)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ t, const int* __restrict__ step, __half* __restrict__ out,
+                                long long ldo, int n, int dim) {
+  const int half_dim = dim >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half_dim) return;
+  const int i = idx / half_dim, j = idx - i * half_dim;
+  const float tv = step ? t[*step] : t[i];
+  const float f = expf(-9.210340371976184f * (float)j / (float)half_dim);
+  const float a = tv * f;
+  out[i * ldo + j] = __float2half_rn(cosf(a));
+  out[i * ldo + half_dim + j] = __float2half_rn(sinf(a));
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int CV) {
+  const long long total = (long long)B * 2 * H * 2 * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
+    const int ox = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    out[i] = x[(((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * CV + cv];
+  }
+}
+
+__global__ void concat_kernel(const uint4* __restrict__ x0, int CV0, const uint4* __restrict__ x1, int CV1,
+                              uint4* __restrict__ out, long long rows) {
+  const int CV = CV0 + CV1;
+  const long long total = rows * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const long long r = i / CV;
+    out[i] = cv < CV0 ? x0[r * CV0 + cv] : x1[r * CV1 + (cv - CV0)];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv_in: NCHW [B,Cin<=8,H,W] -> NHWC [B,H,W,Cout], 3x3 pad 1. thread = (pixel, 8 output channels)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                               const __half* __restrict__ bias, __half* __restrict__ out, int B, int H, int W, int Cin,
+                               int Cout) {
+  extern __shared__ __half s_w[];  // [Cin*9][Cout]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int o = i / K, k = i - o * K;  // w is OIHW: [o][ci][ky][kx] -> k = ci*9 + ky*3 + kx
+    s_w[k * Cout + o] = w[i];
+  }
+  __syncthreads();
+  const int CG = Cout >> 3;
+  const long long total = (long long)B * H * W * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long pix = i / CG;
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+    if (bias) ld8(bias + cg * 8, acc);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    }
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float xv = __half2float(x[(((long long)b * Cin + ci) * H + yy) * W + xx]);
+          float wv[8];
+          ld8(s_w + (ci * 9 + t) * Cout + cg * 8, wv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += xv * wv[e];
+        }
+      }
+    uint4 o;
+    o.x = pack_half2(acc[0], acc[1]);
+    o.y = pack_half2(acc[2], acc[3]);
+    o.z = pack_half2(acc[4], acc[5]);
+    o.w = pack_half2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + pix * Cout + cg * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv_out: NHWC [B,H,W,Cin] -> NCHW [B,Cout<=8,H,W], 3x3 pad 1. One warp per output pixel, lanes over channels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CO_MAX = 8;
+__global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                const __half* __restrict__ bias, __half* __restrict__ out, int B, int H, int W, int Cin,
+                                int Cout) {
+  extern __shared__ __half s_w[];  // [Cout][9][Cin]
+  for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) {
+    const int o = i / (9 * Cin);
+    const int rem = i - o * 9 * Cin;
+    const int t = rem / Cin, ci = rem - t * Cin;
+    s_w[i] = w[((long long)o * Cin + ci) * 9 + t];  // OIHW source
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long npix = (long long)B * H * W;
+  const int CV = Cin >> 3;
+  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < npix;
+       pix += (long long)gridDim.x * warps_per_block) {
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[CO_MAX];
+#pragma unroll
+    for (int o = 0; o < CO_MAX; ++o) acc[o] = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;  // warp-uniform
+      const __half* src = x + (((long long)b * H + yy) * W + xx) * Cin;
+      for (int cv = lane; cv < CV; cv += 32) {
+        float xv[8];
+        ld8(src + cv * 8, xv);
+#pragma unroll
+        for (int o = 0; o < CO_MAX; ++o) {
+          if (o < Cout) {
+            float wv[8];
+            ld8(s_w + (o * 9 + t) * Cin + cv * 8, wv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[o] += xv[e] * wv[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CO_MAX; ++o) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (lane == 0) {
+      for (int o = 0; o < Cout; ++o) {
+        const float bv = bias ? __half2float(bias[o]) : 0.f;
+        out[(((long long)b * Cout + o) * H + yh) * W + xw] = __float2half_rn(acc[o] + bv);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CFG + Euler. Rounding points follow the reference's fp16 tensor arithmetic (custom_pipelines.py:348-350) and
+// diffusers' EulerDiscreteScheduler.step (fp32 inside, result cast back to fp16).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __restrict__ latents,
+                                 __half* __restrict__ model_in, const float* __restrict__ sigmas,
+                                 const int* __restrict__ step, float guidance, long long per_image, int n_images) {
+  const int i = *step;
+  const float sigma = sigmas[i], sigma_next = sigmas[i + 1];
+  const float inv_next = 1.f / sqrtf(sigma_next * sigma_next + 1.f);
+  const long long total = per_image * n_images;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float u = __half2float(noise[idx]);
+    const float c = __half2float(noise[total + idx]);
+    const float d1 = __half2float(__float2half_rn(c - u));
+    const float d2 = __half2float(__float2half_rn(guidance * d1));
+    const float eps = __half2float(__float2half_rn(u + d2));
+    const float x = __half2float(latents[idx]);
+    const float x0 = x - sigma * eps;
+    const float deriv = (x - x0) / sigma;
+    const float xn = x + deriv * (sigma_next - sigma);
+    const __half xh = __float2half_rn(xn);
+    latents[idx] = xh;
+    const __half mi = __float2half_rn(__half2float(xh) * inv_next);
+    model_in[idx] = mi;
+    model_in[total + idx] = mi;
+  }
+}
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
+__global__ void scale_model_input_kernel(const __half* __restrict__ latents, __half* __restrict__ model_in,
+                                         const float* __restrict__ sigmas, const int* __restrict__ step,
+                                         long long total) {
+  const float sigma = sigmas[*step];
+  const float inv = 1.f / sqrtf(sigma * sigma + 1.f);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const __half mi = __float2half_rn(__half2float(latents[idx]) * inv);
+    model_in[idx] = mi;
+    model_in[total + idx] = mi;
+  }
+}
+
+static int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ih
+
+using namespace ih;
+
+extern "C" int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, void* out,
+                                   long long ldo, int M, int N, int K, int act_in, int act_out, void* stream) {
+  IH_CHECK(x && w && out, IH_ERR_ARG, "ih_linear_small_f16: null pointer");
+  IH_CHECK(M >= 1 && M <= SL_MAXM, IH_ERR_SHAPE, "ih_linear_small_f16: M=%d must be in [1,%d]", M, SL_MAXM);
+  IH_CHECK(K % 8 == 0 && ldx % 8 == 0, IH_ERR_ALIGN, "ih_linear_small_f16: K and ldx must be multiples of 8");
+  const int warps = 8;
+  linear_small_kernel<<<(N + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, (const __half*)w, (const __half*)bias, (__half*)out, ldo, M, N, K, act_in, act_out);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_sinusoid_f16(const void* t_f32, const void* step_i32, void* out, long long ldo, int n, int dim,
+                               void* stream) {
+  IH_CHECK(t_f32 && out && dim % 2 == 0, IH_ERR_ARG, "ih_sinusoid_f16: bad arguments");
+  const int total = n * (dim / 2);
+  sinusoid_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)t_f32, (const int*)step_i32,
+                                                                         (__half*)out, ldo, n, dim);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+  IH_CHECK(x && out && C % 8 == 0, IH_ERR_ARG, "ih_upsample2x_f16: bad arguments");
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W,
+                                                                            C / 8);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_concat_f16(const void* x0, int C0, const void* x1, int C1, void* out, long long rows, void* stream) {
+  IH_CHECK(x0 && x1 && out && C0 % 8 == 0 && C1 % 8 == 0, IH_ERR_ARG, "ih_concat_f16: bad arguments");
+  const long long total = rows * ((C0 + C1) / 8);
+  concat_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x0, C0 / 8, (const uint4*)x1,
+                                                                        C1 / 8, (uint4*)out, rows);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_conv_in_f16(const void* x_nchw, const void* w, const void* bias, void* out, int B, int H, int W,
+                              int Cin, int Cout, void* stream) {
+  IH_CHECK(x_nchw && w && out, IH_ERR_ARG, "ih_conv_in_f16: null pointer");
+  IH_CHECK(Cin <= 8 && Cout % 8 == 0 && Cin * 9 * Cout * 2 <= 48 * 1024, IH_ERR_SHAPE, "ih_conv_in_f16: bad shape");
+  const long long total = (long long)B * H * W * (Cout / 8);
+  conv_in_kernel<<<grid_for(total, 256), 256, Cin * 9 * Cout * 2, (cudaStream_t)stream>>>(
+      (const __half*)x_nchw, (const __half*)w, (const __half*)bias, (__half*)out, B, H, W, Cin, Cout);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_conv_out_f16(const void* x, const void* w, const void* bias, void* out_nchw, int B, int H, int W,
+                               int Cin, int Cout, void* stream) {
+  IH_CHECK(x && w && out_nchw, IH_ERR_ARG, "ih_conv_out_f16: null pointer");
+  IH_CHECK(Cout <= CO_MAX && Cin % 8 == 0 && Cout * 9 * Cin * 2 <= 48 * 1024, IH_ERR_SHAPE,
+           "ih_conv_out_f16: bad shape");
+  const long long npix = (long long)B * H * W;
+  long long blocks = (npix + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  conv_out_kernel<<<(int)blocks, 256, Cout * 9 * Cin * 2, (cudaStream_t)stream>>>(
+      (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)out_nchw, B, H, W, Cin, Cout);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int ih_euler_cfg_step(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
+                                 float guidance, long long n_per_image, int n_images, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IH_CHECK(noise_pred && latents && model_in && sigmas && step, IH_ERR_ARG, "ih_euler_cfg_step: null pointer");
+  const long long total = n_per_image * n_images;
+  euler_cfg_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half*)noise_pred, (__half*)latents,
+                                                             (__half*)model_in, (const float*)sigmas,
+                                                             (const int*)step, guidance, n_per_image, n_images);
+  IH_CUDA(cudaGetLastError());
+  step_inc_kernel<<<1, 1, 0, stream>>>((int*)step);
+  IH_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
+extern "C" int ih_scale_model_input(const void* latents, void* model_in, const void* sigmas, const void* step,
+                                    long long total, void* stream) {
+  IH_CHECK(latents && model_in && sigmas && step, IH_ERR_ARG, "ih_scale_model_input: null pointer");
+  scale_model_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, total);
+  IH_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}

@@ -1,0 +1,249 @@
+"""One Python function per C-ABI entry point of libimagharmony_sm100.so (include/ih_api.h).
+
+Tensors are torch CUDA fp16; PyTorch is only used for device memory and the current stream. No op has a
+PyTorch/CPU fallback: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import IHError, check
+
+EPI_NONE, EPI_GEGLU, EPI_SILU = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float16) -> None:
+    if not t.is_cuda:
+        raise IHError(f"{name}: expected a CUDA tensor (the sm_100a path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise IHError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rows(t: torch.Tensor, name: str) -> int:
+    """Row stride (elements) of a 2-D view whose last dim is contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise IHError(f"{name}: expected a 2-D tensor with contiguous last dim, got shape {tuple(t.shape)} "
+                      f"strides {t.stride()}")
+    return t.stride(0)
+
+
+def launch_count() -> int:
+    return int(_lib.load().ih_launch_count())
+
+
+def launch_count_reset() -> None:
+    _lib.load().ih_launch_count_reset()
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
+           rows_per_group: int = 0, geglu: bool = False, silu: bool = False,
+           out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
+    """out = epi(x @ w.T + bias + rowbias[row // rows_per_group]) + residual ; x [M,K], w [N,K] (nn.Linear layout)."""
+    lib = _lib.load()
+    _req(x, "x"); _req(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or not w.is_contiguous():
+        raise IHError(f"linear: weight must be contiguous [N,{K}], got {tuple(w.shape)}")
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
+    ldr = _rows(residual, "residual") if residual is not None else 0
+    ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
+    epi = (EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0)
+    rc = lib.ih_gemm_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(rowbias), rows_per_group, ldrb,
+                         _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _stream())
+    check(rc, "ih_gemm_f16")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+            rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, stride: int = 1,
+            out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
+    """3x3 conv, pad 1. x NHWC [B,H,W,Cin]; w_packed [Cout, 9*Cin] (see pack_conv3x3_weight); rowbias [B, >=Cout]."""
+    lib = _lib.load()
+    _req(x, "x"); _req(w_packed, "w")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    if not x.is_contiguous() or not w_packed.is_contiguous() or w_packed.shape[1] != 9 * Cin:
+        raise IHError("conv3x3: x must be contiguous NHWC and w_packed [Cout, 9*Cin]")
+    Ho, Wo = H // stride, W // stride
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float16, device=x.device)
+    ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
+    if residual is not None and (not residual.is_contiguous() or residual.shape != out.shape):
+        raise IHError("conv3x3: residual must be contiguous and shaped like the output")
+    rc = lib.ih_conv2d_f16(x.data_ptr(), w_packed.data_ptr(), _p(bias), _p(rowbias), ldrb, _p(residual),
+                           out.data_ptr(), B, H, W, Cin, Cout, 3, stride, tile_n, _stream())
+    check(rc, "ih_conv2d_f16")
+    return out
+
+
+def pack_conv3x3_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] (nn.Conv2d) -> [Cout, 9*Cin] tap-major, the layout ih_conv2d_f16 expects."""
+    Cout, Cin, kh, kw = w_oihw.shape
+    assert kh == 3 and kw == 3
+    return w_oihw.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Nq: int, Nk: int, *,
+              n_ip: int = 0, ip_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B*Nq, >=H*64] / k, v [B*Nk, >=H*64] 2-D views (row stride arbitrary); returns [B*Nq, H*64]."""
+    lib = _lib.load()
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    if out is None:
+        out = torch.empty((B * Nq, H * 64), dtype=torch.float16, device=q.device)
+    rc = lib.ih_attention_f16(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                              out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, n_ip, float(ip_scale), _stream())
+    check(rc, "ih_attention_f16")
+    return out
+
+
+_gn_ws = {}
+
+
+def _gn_workspace(device, n_doubles: int) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < n_doubles:
+        ws = torch.empty(max(n_doubles, 4096), dtype=torch.float64, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None,
+              groups: int = 32, eps: float = 1e-5, silu: bool = False, out: Optional[torch.Tensor] = None,
+              ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm over NHWC x0 [B,H,W,C0] (optionally concatenated with x1 [B,H,W,C1] on channels)."""
+    lib = _lib.load()
+    _req(x0, "x0")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    if not x0.is_contiguous() or (x1 is not None and not x1.is_contiguous()):
+        raise IHError("groupnorm: inputs must be contiguous NHWC")
+    if out is None:
+        out = torch.empty((B, H, W, C0 + C1), dtype=torch.float16, device=x0.device)
+    if ws is None:
+        ws = _gn_workspace(x0.device, 2 * B * groups)
+    rc = lib.ih_groupnorm_f16(x0.data_ptr(), C0, _p(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                              ws.data_ptr(), B, H * W, groups, float(eps), int(silu), _stream())
+    check(rc, "ih_groupnorm_f16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, "x")
+    if not x.is_contiguous():
+        raise IHError("layernorm: x must be contiguous")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    rc = lib.ih_layernorm_f16(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, C, float(eps),
+                              _stream())
+    check(rc, "ih_layernorm_f16")
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act_in: bool = False,
+                 act_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Small-M (<= 8 rows) linear with optional SiLU on the input and/or output."""
+    lib = _lib.load()
+    _req(x, "x"); _req(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    rc = lib.ih_linear_small_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), out.data_ptr(),
+                                 _rows(out, "out"), M, N, K, int(act_in), int(act_out), _stream())
+    check(rc, "ih_linear_small_f16")
+    return out
+
+
+def sinusoid(t: torch.Tensor, dim: int, n: int, *, step: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, dim] fp16 sinusoidal embedding of fp32 `t` (or of t[step] for every row when `step` is given)."""
+    lib = _lib.load()
+    _req(t, "t", torch.float32)
+    if out is None:
+        out = torch.empty((n, dim), dtype=torch.float16, device=t.device)
+    rc = lib.ih_sinusoid_f16(t.data_ptr(), _p(step), out.data_ptr(), _rows(out, "out"), n, dim, _stream())
+    check(rc, "ih_sinusoid_f16")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, "x")
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float16, device=x.device)
+    check(lib.ih_upsample2x_f16(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream()), "ih_upsample2x_f16")
+    return out
+
+
+def concat_channels(x0: torch.Tensor, x1: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x0, "x0"); _req(x1, "x1")
+    C0, C1 = x0.shape[-1], x1.shape[-1]
+    rows = x0.numel() // C0
+    if out is None:
+        out = torch.empty(tuple(x0.shape[:-1]) + (C0 + C1,), dtype=torch.float16, device=x0.device)
+    check(lib.ih_concat_f16(x0.data_ptr(), C0, x1.data_ptr(), C1, out.data_ptr(), rows, _stream()), "ih_concat_f16")
+    return out
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    _req(x_nchw, "x")
+    B, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x_nchw.device)
+    check(lib.ih_conv_in_f16(x_nchw.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, H, W, Cin, Cout,
+                             _stream()), "ih_conv_in_f16")
+    return out
+
+
+def conv_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    _req(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, Cout, H, W), dtype=torch.float16, device=x.device)
+    check(lib.ih_conv_out_f16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, H, W, Cin, Cout, _stream()),
+          "ih_conv_out_f16")
+    return out
+
+
+def euler_cfg_step(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor,
+                   step: torch.Tensor, guidance: float) -> None:
+    lib = _lib.load()
+    _req(noise_pred, "noise_pred"); _req(latents, "latents"); _req(model_in, "model_in")
+    _req(sigmas, "sigmas", torch.float32); _req(step, "step", torch.int32)
+    n = latents.shape[0]
+    per = latents.numel() // n
+    check(lib.ih_euler_cfg_step(noise_pred.data_ptr(), latents.data_ptr(), model_in.data_ptr(), sigmas.data_ptr(),
+                                step.data_ptr(), float(guidance), per, n, _stream()), "ih_euler_cfg_step")
+
+
+def scale_model_input(latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor, step: torch.Tensor) -> None:
+    lib = _lib.load()
+    _req(latents, "latents"); _req(model_in, "model_in")
+    check(lib.ih_scale_model_input(latents.data_ptr(), model_in.data_ptr(), sigmas.data_ptr(), step.data_ptr(),
+                                   latents.numel(), _stream()), "ih_scale_model_input")

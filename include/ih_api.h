@@ -1,0 +1,109 @@
+/* libimagharmony_sm100.so -- C ABI of the B200-native SDXL / IMAGHarmony denoise hot path.
+ *
+ * The reference (muzishen/IMAGHarmony) has no FFI of its own: its operator boundary is the diffusers
+ * attention-processor protocol (ip_adapter/attention_processor.py:364-371) and the nn.Module calls inside the
+ * diffusers UNet it drives from ip_adapter/custom_pipelines.py:338-345.  Each entry point below names the reference
+ * call site(s) whose arithmetic it replaces.  The Python host (imagharmony_b200/ops.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - all tensors are fp16 ("__half") device pointers unless stated; activations are NHWC / [rows, channels].
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates, synchronises or keeps state except an
+ *     internally locked TMA-descriptor cache.
+ *   - return 0 on success, <0 on error; ih_last_error() returns a thread-local description.
+ */
+#ifndef IH_API_H
+#define IH_API_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IH_API_VERSION 1
+
+/* epilogue flags for ih_gemm_f16 */
+#define IH_EPI_NONE 0
+#define IH_EPI_GEGLU 1 /* out[:, j] = (acc[:, j] + b[j]) * gelu_erf(acc[:, F + j] + b[F + j]),  N = 2F */
+#define IH_EPI_SILU 2  /* out = silu(acc + bias) */
+
+const char* ih_last_error(void);
+int ih_version(void);
+long long ih_launch_count(void); /* kernels launched by this library since the last reset */
+void ih_launch_count_reset(void);
+
+/* out[M,N] = epi(A[M,K] @ W[N,K]^T + bias[N] + rowbias[row / rows_per_group, N]) + residual[M,N]
+ * Replaces nn.Linear: attention_processor.py:292,299-300,320 (AttnProcessor2_0 to_q/to_k/to_v/to_out),
+ * :396,410-411,432-433,453 (IPAttnProcessor2_0 incl. to_k_ip/to_v_ip), and the diffusers proj_in/proj_out/FF/1x1
+ * conv layers reached through custom_pipelines.py:338-345.  tile_n: 0 = auto, else 64/128/256. */
+int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
+                int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
+                long long ldo, int M, int N, int K, int epilogue, int tile_n, void* stream);
+
+/* 3x3 convolution, padding 1, stride 1|2, NHWC activations, weight [Cout, 9*Cin] (tap-major: (ky*3+kx)*Cin + c).
+ * out = conv(x) + bias[Cout] + rowbias[b*ld_rowbias + c] + residual.  Replaces diffusers ResnetBlock2D / Downsample2D /
+ * Upsample2D nn.Conv2d (custom_pipelines.py:338-345 -> unet forward). */
+int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
+                  const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
+                  int tile_n, void* stream);
+
+/* Multi-head attention, head_dim 64, softmax scale 1/8, no mask.
+ *   q: [B, Nq, *] rows with ldq elements per row, head h at columns [h*64, h*64+64) (same for k, v, out).
+ *   Self attention (n_ip == 0): out = softmax(q k^T / 8) v over Nk keys.
+ *   Decoupled IP cross attention (n_ip > 0): keys/values are the concatenation [text (Nk - n_ip) ; ip (n_ip)];
+ *     out = softmax_text(q k_t^T/8) v_t + ip_scale * softmax_ip(q k_ip^T/8) v_ip   (two separate softmaxes).
+ * Replaces F.scaled_dot_product_attention at attention_processor.py:312-314 (self), :423-425 (text branch),
+ * :440-442 + :450 (IP branch and the scale*ip axpy).  Nk <= 128 uses the single-block path. */
+int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                     void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
+                     void* stream);
+
+/* GroupNorm over NHWC [B, HW, C] (optionally the channel-concatenation of two tensors x0 [.., C0] and x1 [.., C1]),
+ * fp32 statistics, optional fused SiLU.  stats workspace: 2*B*groups doubles (zeroed by the call).
+ * Replaces nn.GroupNorm (+ nn.SiLU) in diffusers ResnetBlock2D / Transformer2DModel. */
+int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void* gamma, const void* beta, void* out,
+                     void* stats_ws, int B, int HW, int groups, float eps, int silu, void* stream);
+
+/* LayerNorm over the last dim of [rows, C], fp32 statistics. Replaces nn.LayerNorm in BasicTransformerBlock. */
+int ih_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int C, float eps,
+                     void* stream);
+
+/* Small-M linear (M <= 8 rows): out[m, n] = act_out(W[n,:] . act_in(x[m,:]) + b[n]); act: 0 none, 1 SiLU.
+ * Time / added-condition embeddings and the 17 time_emb_proj layers (diffusers), ImageProjModel / HarmonyAttention
+ * linears (ip_adapter.py:41-48, train.py:243-266). */
+int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, void* out, long long ldo, int M,
+                        int N, int K, int act_in, int act_out, void* stream);
+
+/* Sinusoidal embedding (flip_sin_to_cos, shift 0): out[i, :] = [cos(t_i f), sin(t_i f)], f = 10000^(-j/half). t fp32.
+ * step_i32 == NULL: t_i = t_f32[i]; else every row uses t_f32[*step_i32] (device-resident step counter, so the
+ * timestep of custom_pipelines.py:325 can live inside a replayed CUDA graph). */
+int ih_sinusoid_f16(const void* t_f32, const void* step_i32, void* out, long long ldo, int n, int dim, void* stream);
+
+/* Nearest-neighbour 2x upsample NHWC [B,H,W,C] -> [B,2H,2W,C]. */
+int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream);
+
+/* Channel concat of two NHWC tensors: out[.., :C0] = x0, out[.., C0:] = x1. rows = B*H*W. */
+int ih_concat_f16(const void* x0, int C0, const void* x1, int C1, void* out, long long rows, void* stream);
+
+/* conv_in: NCHW latent [B,4,H,W] -> NHWC [B,H,W,Cout], 3x3 pad 1 (weight OIHW [Cout,4,3,3]). */
+int ih_conv_in_f16(const void* x_nchw, const void* w, const void* bias, void* out, int B, int H, int W, int Cin,
+                   int Cout, void* stream);
+/* conv_out: NHWC [B,H,W,Cin] -> NCHW [B,Cout,H,W], 3x3 pad 1 (weight OIHW [Cout,Cin,3,3]), Cout <= 8. */
+int ih_conv_out_f16(const void* x, const void* w, const void* bias, void* out_nchw, int B, int H, int W, int Cin,
+                    int Cout, void* stream);
+
+/* One scheduler transition (custom_pipelines.py:332-334,348-357):
+ *   eps = u + g (c - u)  (fp16 tensor arithmetic, rounded like the reference's);
+ *   x <- fp16( x + ((x - (x - sigma_i eps)) / sigma_i) (sigma_{i+1} - sigma_i) )   (fp32 inside, Euler, [3P] diffusers);
+ *   model_in <- cat([x, x]) / sqrt(sigma_{i+1}^2 + 1)  (next step's scaled CFG input); step counter i += 1.
+ * noise_pred: [2n,4,H,W] fp16 (uncond half first), latents: [n,4,H,W] fp16, model_in: [2n,4,H,W] fp16.
+ * sigmas: device fp32 [T+1]; step: device int32 (read, then incremented). n_per_image = 4*H*W. */
+int ih_euler_cfg_step(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
+                      float guidance, long long n_per_image, int n_images, void* stream);
+
+/* model_in = cat([latents, latents]) / sqrt(sigma[*step]^2 + 1)   (custom_pipelines.py:332-334, first step). */
+int ih_scale_model_input(const void* latents, void* model_in, const void* sigmas, const void* step, long long total,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IH_API_H */
