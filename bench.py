@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- denoise-steps/s of the SDXL + IMAGHarmony hot path (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--images n] [--res 1024]
+
+A "step" is one pass of the hot path over one batch: UNet forward on the CFG pair(s) + CFG combine + Euler update
+(custom_pipelines.py:325-363) at 1024x1024 (latent 128x128), random-init SDXL-base weights, synthetic embeddings.
+  value : whole-job denoise-steps/s with inputs resident in HBM (CUDA-graph replays timed with CUDA events)
+  e2e   : same metric through the public call `DenoiseEngine.run(...)` with pinned HOST inputs and a host read of the
+          final latents inside the timed region
+  roofline : the dominant kernel (tcgen05 GEMM, FF GEGLU-in shape) timed alone with CUDA events, against the measured
+          bf16/fp16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on the host cores, bounded sample
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "denoise-steps/s @1024^2 SDXL (UNet + CFG + Euler step, IMAGHarmony IP cross-attention)"
+# algorithmic FLOPs of one UNet forward per CFG pair (SURVEY.md section 8d / BASELINE.md section 3)
+TFLOP_PER_PAIR = {64: 3.179, 96: 7.284, 128: 13.524}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_inputs(cfg, n: int, lat: int, T: int, rank: int):
+    """SURVEY.md section 8d synthetic inputs: per-image CPU generators (rank/slot invariant), N(0,1) embeddings."""
+    from imagharmony_b200.scheduler import EulerDiscreteScheduler
+    ins = EulerDiscreteScheduler().set_timesteps(T).init_noise_sigma
+    seeds = [1000 + rank * n + i for i in range(n)]
+    lat_parts = [torch.randn((1, 4, lat, lat), generator=torch.Generator("cpu").manual_seed(s)) for s in seeds]
+    latents = (torch.cat(lat_parts) * ins).half()
+    g = torch.Generator("cpu").manual_seed(1234)
+    L = 77 + cfg.num_ip_tokens
+    pos = torch.randn(n, L, cfg.cross_attention_dim, generator=g).half()
+    neg = torch.randn(n, L, cfg.cross_attention_dim, generator=g).half()
+    pooled = torch.randn(n, cfg.pooled_embed_dim, generator=g).half()
+    npooled = torch.randn(n, cfg.pooled_embed_dim, generator=g).half()
+    res = lat * 8.0
+    tid = torch.tensor([[res, res, 0.0, 0.0, res, res]] * n)
+    return latents, pos, neg, pooled, npooled, tid
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference's PyTorch path) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_unet_seconds(lat: int, repeats: int, warm: int, budget_s: float = 60.0):
+    """Median seconds of one CFG-pair UNet forward (fp32, all host threads) of the CPU oracle at latent size `lat`."""
+    from imagharmony_b200.config import SDXL_BASE as cfg
+    from oracle import adapter_ref as A
+    from oracle.unet_ref import UNetRef
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.device("meta"):
+        m = UNetRef(cfg)
+    m = m.to_empty(device="cpu")
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.fill_(0.5)
+            else:
+                p.uniform_(-0.02, 0.02)
+    A.install_processors(m, cfg)
+    m.eval()
+    g = torch.Generator("cpu").manual_seed(0)
+    x = torch.randn(2, 4, lat, lat, generator=g)
+    ehs = torch.randn(2, 81, cfg.cross_attention_dim, generator=g)
+    te = torch.randn(2, cfg.pooled_embed_dim, generator=g)
+    tid = torch.tensor([[lat * 8.0, lat * 8.0, 0, 0, lat * 8.0, lat * 8.0]] * 2)
+    times = []
+    t_start = time.time()
+    with torch.no_grad():
+        for i in range(warm + repeats):
+            t0 = time.time()
+            m(x, 500.0, ehs, te, tid)
+            dt = time.time() - t0
+            if i >= warm:
+                times.append(dt)
+            if time.time() - t_start > budget_s and times:
+                break
+    times.sort()
+    return times[len(times) // 2], len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lat_sample = 32  # 256^2 sample: ~0.8 TFLOP per CFG pair
+    steps = max(1, min(args.steps, 4))
+    warm = max(0, min(args.warmup, 1))
+    sec, n = cpu_unet_seconds(lat_sample, steps, warm)
+    # scale the bounded sample to the metric's unit with the algorithmic FLOP ratio (attention grows faster than
+    # linearly, so this flatters the CPU path slightly)
+    flop_sample = 13.524 * (lat_sample / 128.0) ** 2
+    est_step_s = sec * (13.524 / flop_sample)
+    value = args.images / est_step_s
+    cores = os.cpu_count() or 1
+    sample = (f"CPU oracle (port of the reference PyTorch path, fp32, {cores} threads): median of {n} UNet forwards on a "
+              f"CFG pair at {lat_sample * 8}^2, scaled to 1024^2 by the algorithmic FLOP ratio")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": est_step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"single {args.res}x{args.res} edit, {args.steps}-step schedule, {args.images} image(s)"},
+            "cpu_baseline": {"value": value, "unit": "denoise-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------------------
+def build_native(cfg, device):
+    from imagharmony_b200.unet import UNet2DConditionModel
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    with torch.device("meta"):
+        shapes = shapes_of(UNet2DConditionModel(cfg))
+    sd = random_state_dict(shapes, seed=0, device=device)          # generated on the GPU: 2.6 B parameters
+    unet = UNet2DConditionModel.from_state_dict(cfg, sd, device=device)
+    procs = torch.nn.ModuleList(unet.attn_processors.values())
+    procs.load_state_dict(random_state_dict(shapes_of(procs), seed=1, device=device))
+    unet.finalize()
+    return unet
+
+
+def time_dominant_kernel(iters: int = 30):
+    """FF GEGLU-in GEMM (2048 x 10240 x 1280, the largest single launch shape: 27.8 % of step FLOPs) timed alone."""
+    from imagharmony_b200 import ops
+    M, N, K = 2048, 10240, 1280
+    # rotate through enough operand sets to exceed the 126 MB L2 between reuses
+    sets = []
+    for _ in range(6):
+        sets.append((torch.randn(M, K, device="cuda").half(), (torch.randn(N, K, device="cuda") * K ** -0.5).half(),
+                     torch.randn(N, device="cuda").half()))
+    for i in range(3):
+        ops.linear(*sets[i % len(sets)], geglu=True)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        ops.linear(*sets[i % len(sets)], geglu=True)
+    e.record()
+    torch.cuda.synchronize()
+    sec = s.elapsed_time(e) * 1e-3 / iters
+    return 2.0 * M * N * K, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--images", type=int, default=1, help="images (noise candidates) per GPU; UNet batch = 2x (CFG)")
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    from imagharmony_b200 import ops
+    from imagharmony_b200.config import SDXL_BASE as cfg
+    from imagharmony_b200.denoise import DenoiseEngine
+
+    K, W, n = args.steps, max(args.warmup, 3), args.images
+    lat = args.res // 8
+    unet = build_native(cfg, device)
+    eng = DenoiseEngine(unet, use_cuda_graph=True)
+    latents, pos, neg, pooled, npooled, tid = [t.pin_memory() for t in synth_inputs(cfg, n, lat, K, rank)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W steps through the public call (captures the graph, fills caches) -------------------------------
+    ops.launch_count_reset()
+    eng.run(latents, pos, neg, pooled, npooled, tid, K, guidance_scale=5.0, ip_scale=1.0, stop_after=W)
+    torch.cuda.synchronize()
+    launches_per_step = eng.last_launches_per_step
+
+    # ---- device-resident timing: K graph replays, CUDA events, max over ranks -------------------------------------
+    st = eng._buffers(n, lat, lat, pos.shape[1])
+    timesteps, sigmas, _ = eng.tables(K)
+    st["latents"].copy_(latents)
+    st["step"].zero_()
+    ops.scale_model_input(st["latents"], st["model_in"], sigmas, st["step"])
+    graph = next(iter(eng._graphs.values()))
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(K):
+            graph.replay()
+        ev1.record()
+        barrier()
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+
+    # ---- end to end through the public API: pinned host inputs -> H2D -> K steps -> D2H of the result -------------
+    barrier()
+    t0 = time.perf_counter()
+    out = eng.run(latents, pos, neg, pooled, npooled, tid, K, guidance_scale=5.0, ip_scale=1.0)
+    host_out = out.to("cpu", non_blocking=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert torch.isfinite(host_out.float()).all(), "non-finite latents"
+    h2d = sum(t.numel() * t.element_size() for t in (latents, pos, neg, pooled, npooled, tid, tid))
+    d2h = host_out.numel() * host_out.element_size()
+
+    if dist is not None:
+        tt = torch.tensor([dev_s, e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        pk = peaks()
+        flops, ksec = time_dominant_kernel()
+        achieved = flops / ksec / 1e12
+        step_tflop = TFLOP_PER_PAIR.get(lat, 13.524 * (lat / 128.0) ** 2) * n
+        line = {
+            "metric": METRIC, "value": world * n * K / dev_s, "unit": "denoise-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"single {args.res}x{args.res} edit per GPU, {K}-step Euler schedule, "
+                                   f"{n} image(s)/GPU (UNet batch {2 * n}), SDXL-base UNet random-init, 77+4 tokens, "
+                                   f"guidance 5.0, IP scale 1.0",
+                       "l2": "per-step working set (5.2 GB weights) exceeds L2; inputs larger than L2",
+                       "step_tflop_algorithmic": step_tflop,
+                       "step_tflops_achieved": step_tflop * K / dev_s,
+                       "step_frac_of_sustained_peak": step_tflop * K / dev_s / pk["tflops_sustained"],
+                       "cuda_graph": True},
+            "e2e": {"value": world * n * K / e2e_s, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d / K,
+                    "d2h_bytes_per_step": d2h / K, "note": "copies happen once per K-step call; bytes amortised per step"},
+            "gpu_launches": int(launches_per_step * K),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": "gemm_f16_kernel<256,4,GEGLU> 2048x10240x1280 (FF GEGLU-in)",
+                         "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tflops_burst"], "traffic": None, "peak_source": pk["source"]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                sec, cnt = cpu_unet_seconds(32, 2, 1, budget_s=45.0)
+                est = sec * 16.0
+                line["cpu_baseline"] = {"value": n / est, "unit": "denoise-steps/s", "cores": os.cpu_count() or 1,
+                                        "kind": "port",
+                                        "sample": f"CPU oracle fp32, median of {cnt} UNet forwards on a CFG pair at 256^2 "
+                                                  f"scaled x16 (FLOP ratio) to 1024^2"}
+            except Exception as ex:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "denoise-steps/s", "cores": os.cpu_count() or 1,
+                                        "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,8 +27,9 @@ __device__ __forceinline__ void ld8(const __half* p, float (&x)[8]) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SL_MAXM = 8;
 __global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ w,
-                                    const __half* __restrict__ bias, __half* __restrict__ out, long long ldo, int M,
-                                    int N, int K, int act_in, int act_out) {
+                                    const __half* __restrict__ bias, const __half* __restrict__ addend,
+                                    long long ld_add, __half* __restrict__ out, long long ldo, int M, int N, int K,
+                                    int act_in, int act_out) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -63,6 +64,7 @@ __global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx,
     for (int m = 0; m < M; ++m) {
       float y = __half2float(__float2half_rn(acc[m] + b));  // nn.Linear output is fp16 before the activation
       if (act_out == 1) y = silu_f(y);
+      if (addend) y = __half2float(__float2half_rn(y)) + __half2float(addend[m * ld_add + n]);  // fp16 tensor add
       out[m * ldo + n] = __float2half_rn(y);
     }
   }
@@ -224,7 +226,7 @@ __global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __res
                                  const int* __restrict__ step, float guidance, long long per_image, int n_images) {
   const int i = *step;
   const float sigma = sigmas[i], sigma_next = sigmas[i + 1];
-  const float inv_next = 1.f / sqrtf(sigma_next * sigma_next + 1.f);
+  const float den_next = sqrtf(sigma_next * sigma_next + 1.f);
   const long long total = per_image * n_images;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -234,12 +236,14 @@ __global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __res
     const float d2 = __half2float(__float2half_rn(guidance * d1));
     const float eps = __half2float(__float2half_rn(u + d2));
     const float x = __half2float(latents[idx]);
-    const float x0 = x - sigma * eps;
+    // [3P] diffusers: `sample - sigma_hat * model_output` multiplies a 0-dim fp32 sigma with the fp16 model output,
+    // so the product is an fp16 tensor (type promotion keeps the dimensioned tensor's dtype)
+    const float x0 = x - __half2float(__float2half_rn(sigma * eps));
     const float deriv = (x - x0) / sigma;
     const float xn = x + deriv * (sigma_next - sigma);
     const __half xh = __float2half_rn(xn);
     latents[idx] = xh;
-    const __half mi = __float2half_rn(__half2float(xh) * inv_next);
+    const __half mi = __float2half_rn(__half2float(xh) / den_next);
     model_in[idx] = mi;
     model_in[total + idx] = mi;
   }
@@ -250,10 +254,10 @@ __global__ void scale_model_input_kernel(const __half* __restrict__ latents, __h
                                          const float* __restrict__ sigmas, const int* __restrict__ step,
                                          long long total) {
   const float sigma = sigmas[*step];
-  const float inv = 1.f / sqrtf(sigma * sigma + 1.f);
+  const float den = sqrtf(sigma * sigma + 1.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const __half mi = __float2half_rn(__half2float(latents[idx]) * inv);
+    const __half mi = __float2half_rn(__half2float(latents[idx]) / den);
     model_in[idx] = mi;
     model_in[total + idx] = mi;
   }
@@ -271,16 +275,22 @@ static int grid_for(long long total, int threads) {
 
 using namespace ih;
 
-extern "C" int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, void* out,
-                                   long long ldo, int M, int N, int K, int act_in, int act_out, void* stream) {
+extern "C" int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, const void* addend,
+                                   long long ld_add, void* out, long long ldo, int M, int N, int K, int act_in,
+                                   int act_out, void* stream) {
   IH_CHECK(x && w && out, IH_ERR_ARG, "ih_linear_small_f16: null pointer");
-  IH_CHECK(M >= 1 && M <= SL_MAXM, IH_ERR_SHAPE, "ih_linear_small_f16: M=%d must be in [1,%d]", M, SL_MAXM);
+  IH_CHECK(M >= 1 && M <= 64, IH_ERR_SHAPE, "ih_linear_small_f16: M=%d must be in [1,64] (use ih_gemm_f16)", M);
   IH_CHECK(K % 8 == 0 && ldx % 8 == 0, IH_ERR_ALIGN, "ih_linear_small_f16: K and ldx must be multiples of 8");
   const int warps = 8;
-  linear_small_kernel<<<(N + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (const __half*)w, (const __half*)bias, (__half*)out, ldo, M, N, K, act_in, act_out);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  for (int m0 = 0; m0 < M; m0 += SL_MAXM) {  // row chunks of 8 (W is re-read from L2 for the later chunks)
+    const int mc = (M - m0) < SL_MAXM ? (M - m0) : SL_MAXM;
+    linear_small_kernel<<<(N + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+        (const __half*)x + m0 * ldx, ldx, (const __half*)w, (const __half*)bias,
+        addend ? (const __half*)addend + m0 * ld_add : nullptr, ld_add, (__half*)out + m0 * ldo, ldo, mc, N, K,
+        act_in, act_out);
+    IH_CUDA(cudaGetLastError());
+    count_launch();
+  }
   return 0;
 }
 

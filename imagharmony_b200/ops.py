@@ -111,18 +111,6 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int,
     return out
 
 
-_gn_ws = {}
-
-
-def _gn_workspace(device, n_doubles: int) -> torch.Tensor:
-    key = (device, torch.cuda.current_stream().cuda_stream)
-    ws = _gn_ws.get(key)
-    if ws is None or ws.numel() < n_doubles:
-        ws = torch.empty(max(n_doubles, 4096), dtype=torch.float64, device=device)
-        _gn_ws[key] = ws
-    return ws
-
-
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None,
               groups: int = 32, eps: float = 1e-5, silu: bool = False, out: Optional[torch.Tensor] = None,
               ws: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -135,8 +123,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: 
         raise IHError("groupnorm: inputs must be contiguous NHWC")
     if out is None:
         out = torch.empty((B, H, W, C0 + C1), dtype=torch.float16, device=x0.device)
-    if ws is None:
-        ws = _gn_workspace(x0.device, 2 * B * groups)
+    if ws is None:   # tiny per-call statistics workspace (comes from the graph's private pool under capture)
+        ws = torch.empty(2 * B * groups, dtype=torch.float64, device=x0.device)
     rc = lib.ih_groupnorm_f16(x0.data_ptr(), C0, _p(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
                               ws.data_ptr(), B, H * W, groups, float(eps), int(silu), _stream())
     check(rc, "ih_groupnorm_f16")
@@ -160,16 +148,20 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act_in: bool = False,
-                 act_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Small-M (<= 8 rows) linear with optional SiLU on the input and/or output."""
+                 act_out: bool = False, addend: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Small-M (<= 8 rows) linear with optional SiLU on the input and/or output and an optional fp16 addend."""
     lib = _lib.load()
     _req(x, "x"); _req(w, "w")
     M, K = x.shape
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float16, device=x.device)
-    rc = lib.ih_linear_small_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), out.data_ptr(),
-                                 _rows(out, "out"), M, N, K, int(act_in), int(act_out), _stream())
+    if M > 64:
+        raise IHError(f"linear_small: M={M} > 64 rows; use ops.linear")
+    ld_add = _rows(addend, "addend") if addend is not None else 0
+    rc = lib.ih_linear_small_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(addend), ld_add,
+                                 out.data_ptr(), _rows(out, "out"), M, N, K, int(act_in), int(act_out), _stream())
     check(rc, "ih_linear_small_f16")
     return out
 

@@ -1,0 +1,412 @@
+"""SDXL UNet2DConditionModel running on the sm_100a kernel library.
+
+Same module tree / state-dict keys / `attn_processors` + `set_attn_processor` surface as the diffusers model the
+reference drives (ip_adapter.py:102,125; custom_pipelines.py:338-345), but the forward pass is a sequence of C-ABI
+kernel launches on NHWC fp16 activations:
+
+    conv_in -> [ResBlock: GN+SiLU -> conv3x3(+temb) -> GN+SiLU -> conv3x3(+shortcut/residual)]
+            -> [Transformer2D: GN -> proj_in -> N x (LN -> fused-QKV GEMM -> attention -> out GEMM(+res);
+                                                    LN -> q GEMM -> decoupled IP cross attention -> out GEMM(+res);
+                                                    LN -> GEGLU GEMM -> FF-out GEMM(+res)) -> proj_out(+res)]
+            -> ... -> GN+SiLU -> conv_out
+
+nn.Linear / nn.Conv2d / nn.GroupNorm / nn.LayerNorm instances are used purely as parameter containers (their own
+forward is never called); kernel-layout copies (tap-major conv weights, fused QKV / KV matrices, the concatenated
+time_emb_proj matrix) are derived once in `finalize()`.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import IHError
+from .config import UNetConfig
+
+
+class Attention(nn.Module):
+    """Parameter shell with the attributes the reference processors read (attention_processor.py:374-463)."""
+
+    def __init__(self, query_dim: int, heads: int, cross_attention_dim: Optional[int] = None):
+        super().__init__()
+        kv_dim = cross_attention_dim or query_dim
+        self.heads = heads
+        self.is_cross = cross_attention_dim is not None
+        self.to_q = nn.Linear(query_dim, query_dim, bias=False)
+        self.to_k = nn.Linear(kv_dim, query_dim, bias=False)
+        self.to_v = nn.Linear(kv_dim, query_dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(query_dim, query_dim), nn.Dropout(0.0)])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = False
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.processor = None
+        self._w_qkv = None
+        self._w_kv = None
+
+    def fused_qkv_weight(self) -> torch.Tensor:
+        if self._w_qkv is None:
+            self._w_qkv = torch.cat([self.to_q.weight.detach(), self.to_k.weight.detach(),
+                                     self.to_v.weight.detach()], dim=0).contiguous()
+        return self._w_qkv
+
+    def fused_kv_weight(self) -> torch.Tensor:
+        if self._w_kv is None:
+            self._w_kv = torch.cat([self.to_k.weight.detach(), self.to_v.weight.detach()], dim=0).contiguous()
+        return self._w_kv
+
+    def drop_fused(self):
+        self._w_qkv = None
+        self._w_kv = None
+
+    def forward(self, hidden_states, encoder_hidden_states=None, residual=None):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states, attention_mask=None,
+                              residual=residual)
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin: int, cout: int, temb_dim: int, groups: int):
+        super().__init__()
+        self.cin, self.cout, self.groups = cin, cout, groups
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-5)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_dim, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-5)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self._w1 = self._w2 = self._wsc = None
+        self.temb_offset = 0   # column offset of this block inside the concatenated time_emb_proj output
+
+    def finalize(self):
+        self._w1 = ops.pack_conv3x3_weight(self.conv1.weight.detach())
+        self._w2 = ops.pack_conv3x3_weight(self.conv2.weight.detach())
+        if self.conv_shortcut is not None:
+            self._wsc = self.conv_shortcut.weight.detach().reshape(self.cout, self.cin).contiguous()
+
+    def forward(self, x: torch.Tensor, temb_all: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x NHWC [B,H,W,C0] (+ skip [B,H,W,C1] concatenated on channels); temb_all [B, sum(Cout)]."""
+        B, H, W, _ = x.shape
+        h = ops.groupnorm(x, self.norm1.weight, self.norm1.bias, x1=skip, groups=self.groups, eps=1e-5, silu=True)
+        temb = temb_all[:, self.temb_offset:self.temb_offset + self.cout]
+        h = ops.conv3x3(h, self._w1, self.conv1.bias, rowbias=temb)
+        h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=1e-5, silu=True)
+        if self.conv_shortcut is not None:
+            xin = x if skip is None else ops.concat_channels(x, skip)
+            sc = ops.linear(xin.reshape(B * H * W, self.cin), self._wsc, self.conv_shortcut.bias)
+            sc = sc.reshape(B, H, W, self.cout)
+        else:
+            if skip is not None:
+                raise IHError("ResnetBlock2D: concatenated input needs a conv_shortcut")
+            sc = x
+        return ops.conv3x3(h, self._w2, self.conv2.bias, residual=sc)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim: int, heads: int, cross_dim: int):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn1 = Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn2 = Attention(dim, heads, cross_dim)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.ff = FeedForward(dim)
+
+    def forward(self, h: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
+        """h [B, N, C] tokens."""
+        B, N, C = h.shape
+        n = ops.layernorm(h, self.norm1.weight, self.norm1.bias, 1e-5)
+        h = self.attn1(n, None, residual=h)
+        n = ops.layernorm(h, self.norm2.weight, self.norm2.bias, 1e-5)
+        h = self.attn2(n, ehs, residual=h)
+        n = ops.layernorm(h, self.norm3.weight, self.norm3.bias, 1e-5)
+        g = ops.linear(n.reshape(B * N, C), self.ff.net[0].proj.weight, self.ff.net[0].proj.bias, geglu=True)
+        h2 = ops.linear(g, self.ff.net[2].weight, self.ff.net[2].bias, residual=h.reshape(B * N, C))
+        return h2.reshape(B, N, C)
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, dim: int, heads: int, depth: int, cross_dim: int, groups: int):
+        super().__init__()
+        self.groups = groups
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, cross_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(dim, dim)
+
+    def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = x.shape
+        h = ops.groupnorm(x, self.norm.weight, self.norm.bias, groups=self.groups, eps=1e-6, silu=False)
+        h = ops.linear(h.reshape(B * H * W, C), self.proj_in.weight, self.proj_in.bias).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            h = blk(h, ehs)
+        out = ops.linear(h.reshape(B * H * W, C), self.proj_out.weight, self.proj_out.bias,
+                         residual=x.reshape(B * H * W, C))
+        return out.reshape(B, H, W, C)
+
+
+class Resample(nn.Module):
+    def __init__(self, ch: int, up: bool):
+        super().__init__()
+        self.up = up
+        self.conv = nn.Conv2d(ch, ch, 3, stride=1 if up else 2, padding=1)
+        self._w = None
+
+    def finalize(self):
+        self._w = ops.pack_conv3x3_weight(self.conv.weight.detach())
+
+    def forward(self, x):
+        if self.up:
+            return ops.conv3x3(ops.upsample2x(x), self._w, self.conv.bias)
+        return ops.conv3x3(x, self._w, self.conv.bias, stride=2)
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, cin: int, cout: int, depth: int, add_down: bool):
+        super().__init__()
+        temb = cfg.time_embed_dim
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if j == 0 else cout, cout, temb, cfg.norm_num_groups)
+                                      for j in range(cfg.layers_per_block)])
+        self.has_attn = depth > 0
+        if self.has_attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, cfg.heads(cout), depth, cfg.cross_attention_dim,
+                                                                cfg.norm_num_groups)
+                                             for _ in range(cfg.layers_per_block)])
+        self.has_down = add_down
+        if add_down:
+            self.downsamplers = nn.ModuleList([Resample(cout, up=False)])
+
+    def forward(self, x, temb_all, ehs, skips: List[torch.Tensor]):
+        for j, res in enumerate(self.resnets):
+            x = res(x, temb_all)
+            if self.has_attn:
+                x = self.attentions[j](x, ehs)
+            skips.append(x)
+        if self.has_down:
+            x = self.downsamplers[0](x)
+            skips.append(x)
+        return x
+
+
+class MidBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, ch: int, depth: int):
+        super().__init__()
+        temb = cfg.time_embed_dim
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb, cfg.norm_num_groups) for _ in range(2)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, cfg.heads(ch), depth, cfg.cross_attention_dim,
+                                                            cfg.norm_num_groups)])
+
+    def forward(self, x, temb_all, ehs):
+        x = self.resnets[0](x, temb_all)
+        x = self.attentions[0](x, ehs)
+        return self.resnets[1](x, temb_all)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, prev_out: int, skip_ch: int, cout: int, depth: int, add_up: bool):
+        super().__init__()
+        temb = cfg.time_embed_dim
+        n = cfg.layers_per_block + 1
+        res = []
+        for j in range(n):
+            res_skip = skip_ch if j == n - 1 else cout
+            res_in = prev_out if j == 0 else cout
+            res.append(ResnetBlock2D(res_in + res_skip, cout, temb, cfg.norm_num_groups))
+        self.resnets = nn.ModuleList(res)
+        self.has_attn = depth > 0
+        if self.has_attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, cfg.heads(cout), depth, cfg.cross_attention_dim,
+                                                                cfg.norm_num_groups) for _ in range(n)])
+        self.has_up = add_up
+        if add_up:
+            self.upsamplers = nn.ModuleList([Resample(cout, up=True)])
+
+    def forward(self, x, temb_all, ehs, skips: List[torch.Tensor]):
+        for j, res in enumerate(self.resnets):
+            x = res(x, temb_all, skip=skips.pop())     # GN / shortcut read the two tensors; no standalone concat
+            if self.has_attn:
+                x = self.attentions[j](x, ehs)
+        if self.has_up:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim: int, dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class UNet2DConditionModel(nn.Module):
+    """Native SDXL UNet. Build on the meta device + `load_state_dict(..., assign=True)` or via `from_state_dict`."""
+
+    def __init__(self, cfg: UNetConfig):
+        super().__init__()
+        self.config = cfg
+        boc = cfg.block_out_channels
+        tl = cfg.transformer_layers_per_block
+        self.conv_in = nn.Conv2d(cfg.in_channels, boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], cfg.time_embed_dim)
+        self.add_embedding = TimestepEmbedding(cfg.add_embed_in, cfg.time_embed_dim)
+        downs = []
+        ch = boc[0]
+        for i, co in enumerate(boc):
+            downs.append(DownBlock(cfg, ch, co, tl[i], add_down=i < len(boc) - 1))
+            ch = co
+        self.down_blocks = nn.ModuleList(downs)
+        rev = list(reversed(boc))
+        rtl = list(reversed(tl))
+        ups = []
+        prev = rev[0]
+        for i, co in enumerate(rev):
+            skip_ch = rev[min(i + 1, len(rev) - 1)]
+            ups.append(UpBlock(cfg, prev, skip_ch, co, rtl[i], add_up=i < len(rev) - 1))
+            prev = co
+        self.up_blocks = nn.ModuleList(ups)
+        self.mid_block = MidBlock(cfg, boc[-1], tl[-1])
+        self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, boc[0], eps=1e-5)
+        self.conv_out = nn.Conv2d(boc[0], cfg.out_channels, 3, padding=1)
+        self._w_temb = None
+        self._b_temb = None
+        self._aug = None          # (key, aug_emb [B, time_embed_dim])
+        self._text_only = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, cfg: UNetConfig, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        with torch.device("meta"):
+            m = cls(cfg)
+        sd = {k: v.to(device=device, dtype=torch.float16) for k, v in state_dict.items()}
+        m.load_state_dict(sd, assign=True)
+        m.requires_grad_(False)
+        m.install_default_processors()
+        m.finalize()
+        return m
+
+    def install_default_processors(self, scale: float = 1.0):
+        """IPAdapter.set_ip_adapter (ip_adapter.py:99-125) for this UNet; IP weights are zero until loaded."""
+        from ip_adapter.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
+        cfg = self.config
+        procs = {}
+        dev = self.conv_in.weight.device
+        for name, attn in self._attn_modules():
+            if name.endswith("attn1"):
+                procs[name + ".processor"] = AttnProcessor2_0()
+            else:
+                C = attn.to_q.weight.shape[0]
+                with torch.device("meta"):
+                    p = IPAttnProcessor2_0(C, cfg.cross_attention_dim, scale=scale, num_tokens=cfg.num_ip_tokens,
+                                           skip=cfg.ip_target_substring not in name)
+                p = p.to_empty(device=dev).half()
+                for q in p.parameters():
+                    q.data.zero_()
+                    q.requires_grad_(False)
+                procs[name + ".processor"] = p
+        self.set_attn_processor(procs)
+        return procs
+
+    def _attn_modules(self):
+        for name, m in self.named_modules():
+            if isinstance(m, Attention):
+                yield name, m
+
+    @property
+    def attn_processors(self) -> Dict[str, object]:
+        return {f"{name}.processor": m.processor for name, m in self._attn_modules()}
+
+    def set_attn_processor(self, procs) -> None:
+        for name, m in self._attn_modules():
+            m.processor = procs[f"{name}.processor"] if isinstance(procs, dict) else procs
+
+    def finalize(self):
+        """Derive kernel-layout weights. Call after (re)loading parameters."""
+        offs = 0
+        ws, bs = [], []
+        for m in self.modules():
+            if isinstance(m, (ResnetBlock2D, Resample)):
+                m.finalize()
+            if isinstance(m, ResnetBlock2D):
+                m.temb_offset = offs
+                offs += m.cout
+                ws.append(m.time_emb_proj.weight.detach())
+                bs.append(m.time_emb_proj.bias.detach())
+            if isinstance(m, Attention):
+                m.drop_fused()
+                (m.fused_kv_weight() if m.is_cross else m.fused_qkv_weight())
+        self._w_temb = torch.cat(ws, 0).contiguous()
+        self._b_temb = torch.cat(bs, 0).contiguous()
+        self._aug = None
+        for p in self.attn_processors.values():
+            if hasattr(p, "invalidate"):
+                p.invalidate()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare_conditioning(self, encoder_hidden_states: torch.Tensor, text_embeds: torch.Tensor,
+                             time_ids: torch.Tensor) -> None:
+        """Everything that does not depend on the step: cross-attention K/V of all 70 attn2 layers (text and image
+        tokens) and the text_time additional embedding."""
+        cfg = self.config
+        ehs = encoder_hidden_states
+        B, L, _ = ehs.shape
+        n_text = L - cfg.num_ip_tokens
+        text_only = ehs[:, :n_text].contiguous()
+        self._text_only = text_only
+        for name, attn in self._attn_modules():
+            if attn.is_cross and hasattr(attn.processor, "prepare"):
+                attn.processor.prepare(attn, ehs, text_only=text_only)
+        tid = ops.sinusoid(time_ids.reshape(-1).float().contiguous(), cfg.addition_time_embed_dim, B * 6)
+        add_in = torch.cat([text_embeds.to(torch.float16), tid.reshape(B, -1)], dim=-1).contiguous()
+        h = ops.linear_small(add_in, self.add_embedding.linear_1.weight, self.add_embedding.linear_1.bias, act_out=True)
+        prev = self._aug[1] if (self._aug is not None and self._aug[1].shape[0] == B) else None   # keep the address
+        aug = ops.linear_small(h, self.add_embedding.linear_2.weight, self.add_embedding.linear_2.bias, out=prev)
+        self._aug = ((text_embeds.data_ptr(), time_ids.data_ptr(), B), aug)
+
+    def time_embeddings(self, timesteps: torch.Tensor, step: Optional[torch.Tensor], B: int) -> torch.Tensor:
+        """-> temb_all [B, sum(Cout)]: every ResBlock's time_emb_proj(silu(emb)) in one launch."""
+        cfg = self.config
+        t_in = ops.sinusoid(timesteps, cfg.block_out_channels[0], B, step=step)
+        h = ops.linear_small(t_in, self.time_embedding.linear_1.weight, self.time_embedding.linear_1.bias, act_out=True)
+        emb = ops.linear_small(h, self.time_embedding.linear_2.weight, self.time_embedding.linear_2.bias,
+                               addend=self._aug[1])
+        return ops.linear_small(emb, self._w_temb, self._b_temb, act_in=True)
+
+    def forward(self, sample: torch.Tensor, timesteps: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                text_embeds: Optional[torch.Tensor] = None, time_ids: Optional[torch.Tensor] = None,
+                step: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sample NCHW fp16 [B,4,H,W]; timesteps fp32 device tensor ([B] values, or the whole schedule when `step`
+        -- a device int32 index -- is given); returns noise prediction NCHW fp16."""
+        if self._w_temb is None:
+            raise IHError("UNet2DConditionModel.finalize() has not been called")
+        B = sample.shape[0]
+        key = None if text_embeds is None else (text_embeds.data_ptr(), time_ids.data_ptr(), B)
+        if self._aug is None or (key is not None and self._aug[0] != key):
+            if text_embeds is None:
+                raise IHError("forward() needs text_embeds/time_ids (or a prior prepare_conditioning())")
+            self.prepare_conditioning(encoder_hidden_states, text_embeds, time_ids)
+        temb_all = self.time_embeddings(timesteps, step, B)
+        x = ops.conv_in(sample, self.conv_in.weight, self.conv_in.bias)
+        skips = [x]
+        ehs = encoder_hidden_states
+        for blk in self.down_blocks:
+            x = blk(x, temb_all, ehs, skips)
+        x = self.mid_block(x, temb_all, ehs)
+        for blk in self.up_blocks:
+            x = blk(x, temb_all, ehs, skips)
+        x = ops.groupnorm(x, self.conv_norm_out.weight, self.conv_norm_out.bias, groups=self.config.norm_num_groups,
+                          eps=1e-5, silu=True)
+        return ops.conv_out(x, self.conv_out.weight, self.conv_out.bias)

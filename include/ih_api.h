@@ -66,11 +66,12 @@ int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void*
 int ih_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int C, float eps,
                      void* stream);
 
-/* Small-M linear (M <= 8 rows): out[m, n] = act_out(W[n,:] . act_in(x[m,:]) + b[n]); act: 0 none, 1 SiLU.
+/* Small-M linear (M <= 8 rows): out[m, n] = act_out(W[n,:] . act_in(x[m,:]) + b[n]) + addend[m, n]; act: 0 none, 1 SiLU.
  * Time / added-condition embeddings and the 17 time_emb_proj layers (diffusers), ImageProjModel / HarmonyAttention
  * linears (ip_adapter.py:41-48, train.py:243-266). */
-int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, void* out, long long ldo, int M,
-                        int N, int K, int act_in, int act_out, void* stream);
+int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, const void* addend,
+                        long long ld_add, void* out, long long ldo, int M, int N, int K, int act_in, int act_out,
+                        void* stream);
 
 /* Sinusoidal embedding (flip_sin_to_cos, shift 0): out[i, :] = [cos(t_i f), sin(t_i f)], f = 10000^(-j/half). t fp32.
  * step_i32 == NULL: t_i = t_f32[i]; else every row uses t_f32[*step_i32] (device-resident step counter, so the

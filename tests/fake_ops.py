@@ -1,0 +1,159 @@
+"""TEST-ONLY stand-ins for imagharmony_b200.ops implemented with plain PyTorch on the CPU (fp32).  They let the CPU test
+suite validate the *wiring* of the native UNet / processors / denoise loop (layouts, skip order, weight packing, K/V
+caching) against the oracle without a GPU.  Never imported by the product."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+_count = [0]
+
+
+def launch_count():
+    return _count[0]
+
+
+def launch_count_reset():
+    _count[0] = 0
+
+
+def _f(t):
+    return None if t is None else t.float()
+
+
+def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, out=None,
+           tile_n=0):
+    _count[0] += 1
+    y = x.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if geglu:
+        a, g = y.chunk(2, dim=-1)
+        y = a * F.gelu(g)
+    if rowbias is not None:
+        y = y + rowbias.float().repeat_interleave(rows_per_group, dim=0)
+    if silu:
+        y = F.silu(y)
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def pack_conv3x3_weight(w):
+    Cout, Cin, _, _ = w.shape
+    return w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+
+
+def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, out=None, tile_n=0):
+    _count[0] += 1
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    w = w_packed.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).float()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, _f(bias), stride=stride, padding=1).permute(0, 2, 3, 1)
+    if rowbias is not None:
+        y = y + rowbias.float()[:, None, None, :]
+    if residual is not None:
+        y = y + residual.float()
+    return y.to(x.dtype).contiguous()
+
+
+def attention(q, k, v, B, H, Nq, Nk, *, n_ip=0, ip_scale=1.0, out=None):
+    _count[0] += 1
+    C = H * 64
+    qf = q.float().reshape(B, Nq, H, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Nk, H, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Nk, H, 64).transpose(1, 2)
+    nt = Nk - n_ip
+    o = torch.softmax(qf @ kf[:, :, :nt].transpose(-1, -2) / 8.0, -1) @ vf[:, :, :nt]
+    if n_ip > 0:
+        o = o + ip_scale * (torch.softmax(qf @ kf[:, :, nt:].transpose(-1, -2) / 8.0, -1) @ vf[:, :, nt:])
+    return o.transpose(1, 2).reshape(B * Nq, C).to(q.dtype)
+
+
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, out=None, ws=None):
+    _count[0] += 2
+    x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    y = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma.float(), beta.float(), eps)
+    if silu:
+        y = F.silu(y)
+    return y.permute(0, 2, 3, 1).to(x0.dtype).contiguous()
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _count[0] += 1
+    return F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps).to(x.dtype)
+
+
+def linear_small(x, w, bias=None, *, act_in=False, act_out=False, addend=None, out=None):
+    _count[0] += 1
+    xi = F.silu(x.float()) if act_in else x.float()
+    y = xi @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if act_out:
+        y = F.silu(y)
+    if addend is not None:
+        y = y + addend.float()
+    y = y.to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def sinusoid(t, dim, n, *, step=None, out=None):
+    _count[0] += 1
+    half = dim // 2
+    tv = t[step.long()].expand(n) if step is not None else t[:n]
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    a = tv.float().reshape(-1, 1) * f.reshape(1, -1)
+    return torch.cat([a.cos(), a.sin()], -1).to(torch.float32 if FP32 else torch.float16)
+
+
+FP32 = True
+
+
+def upsample2x(x, out=None):
+    _count[0] += 1
+    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).contiguous()
+
+
+def concat_channels(x0, x1, out=None):
+    _count[0] += 1
+    return torch.cat([x0, x1], dim=-1)
+
+
+def conv_in(x_nchw, w, bias, out=None):
+    _count[0] += 1
+    return F.conv2d(x_nchw.float(), w.float(), _f(bias), padding=1).permute(0, 2, 3, 1).to(x_nchw.dtype).contiguous()
+
+
+def conv_out(x, w, bias, out=None):
+    _count[0] += 1
+    return F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), _f(bias), padding=1).to(x.dtype).contiguous()
+
+
+def euler_cfg_step(noise_pred, latents, model_in, sigmas, step, guidance):
+    _count[0] += 2
+    i = int(step.item())
+    s, sn = float(sigmas[i]), float(sigmas[i + 1])
+    u, c = noise_pred.chunk(2)
+    eps = u + guidance * (c - u)
+    x = latents.float()
+    x0 = x - (s * eps.float()).to(eps.dtype).float()
+    xn = (x + (x - x0) / s * (sn - s)).to(latents.dtype)
+    latents.copy_(xn)
+    mi = (xn.float() / (sn * sn + 1) ** 0.5).to(model_in.dtype)
+    model_in.copy_(torch.cat([mi, mi]))
+    step += 1
+
+
+def scale_model_input(latents, model_in, sigmas, step):
+    _count[0] += 1
+    s = float(sigmas[int(step.item())])
+    mi = (latents.float() / (s * s + 1) ** 0.5).to(model_in.dtype)
+    model_in.copy_(torch.cat([mi, mi]))

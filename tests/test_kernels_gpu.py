@@ -273,7 +273,7 @@ def test_euler_cfg_step(ops):
     u, c = noise.chunk(2)
     eps = u + 5.0 * (c - u)            # fp16 tensor arithmetic like custom_pipelines.py:348-350
     x = lat_ref.float()
-    x0 = x - sig[1] * eps
+    x0 = x - (sig[1] * eps.float()).half().float()   # diffusers: 0-dim fp32 sigma * fp16 tensor -> fp16 product
     d = (x - x0) / sig[1]
     xn = (x + d * (sig[2] - sig[1])).half()
     assert int(step.item()) == 2
