@@ -32,6 +32,7 @@ SIGNATURES = {
                                  c_longlong, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ih_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_float, c_int, c_void_p]),
+    "ih_groupnorm_workspace_bytes": (c_longlong, [c_int, c_int]),
     "ih_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "ih_linear_small_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),

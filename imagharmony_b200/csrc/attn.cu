@@ -292,6 +292,288 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_f16_kernel(const __grid_c
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+
+// ================================================================================================================
+// v2: ping-pong flash attention.  One CTA = 256 query rows (two 128-row tiles A/B) of one (batch, head); 10 warps:
+// warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax of tile A, warps 6-9 softmax of tile B.  While one tile's
+// softmax runs on the CUDA cores / MUFU, the tensor core executes the other tile's S = Q K^T and O += P V.
+// O stays in TMEM across KV blocks (accumulating MMA); the running max is only raised when it grew by more than 2^8
+// ("lazy rescale"), in which case the row thread rescales its O row in TMEM (tcgen05.ld / tcgen05.st).
+// ================================================================================================================
+constexpr int A2_THREADS = 320;
+constexpr int A2_KS = 3;  // K / V stages
+constexpr int A2_SMEM_TILES = ATT_TILE * (2 + 2 * A2_KS) + 4 * ATT_TILE;  // Q_A Q_B | K[KS] | V[KS] | P_A P_B
+constexpr int A2_SMEM_BYTES = A2_SMEM_TILES + 256;
+
+__global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                                  // 2 tiles
+  uint8_t* sK = smem + 2 * ATT_TILE;                   // A2_KS stages
+  uint8_t* sV = sK + A2_KS * ATT_TILE;                 // A2_KS stages
+  uint8_t* sP = sV + A2_KS * ATT_TILE;                 // 2 tiles x 2 key halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_SMEM_TILES);
+  uint64_t* q_full = bars;                  // [2]
+  uint64_t* k_full = bars + 2;              // [KS]
+  uint64_t* k_empty = k_full + A2_KS;       // [KS]
+  uint64_t* v_full = k_empty + A2_KS;       // [KS]
+  uint64_t* v_empty = v_full + A2_KS;       // [KS]
+  uint64_t* s_full = v_empty + A2_KS;       // [2]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_full = p_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nb = p.num_kv_blocks;
+  const bool tileB_active = (q0 + 128) < p.Nq;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    for (int s = 0; s < A2_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&q_full[0], ATT_TILE);
+      tma_load_3d(sQ, &tmQ, &q_full[0], head * 64, q0, b);
+      if (tileB_active) {
+        mbar_arrive_expect_tx(&q_full[1], ATT_TILE);
+        tma_load_3d(sQ + ATT_TILE, &tmQ, &q_full[1], head * 64, q0 + 128, b);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], ATT_TILE);
+        tma_load_3d(sK + s * ATT_TILE, &tmK, &k_full[s], head * 64, j * 128, b);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], ATT_TILE);
+        tma_load_3d(sV + s * ATT_TILE, &tmV, &v_full[s], head * 64, j * 128, b);
+        if (++s == A2_KS) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
+      const int ntiles = tileB_active ? 2 : 1;
+      uint64_t q_desc[2];
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&q_full[t], 0);
+        q_desc[t] = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE));
+      }
+      auto issue_s = [&](int t, int stage) {
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + stage * ATT_TILE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + t * 128, q_desc[t] + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int stage, bool accumulate) {
+        const uint32_t v_addr = smem_u32(sV + stage * ATT_TILE);
+        const uint32_t p_addr = smem_u32(sP + t * 2 * ATT_TILE);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t p_desc = umma_desc_sw128(p_addr + (kk >> 2) * ATT_TILE) + 2 * (kk & 3);
+          const uint64_t v_desc = umma_desc_sw128(v_addr + kk * 2048);
+          umma_f16_ss(tmem_base + 256 + t * 64, p_desc, v_desc, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
+        }
+      };
+      // prologue: S(0) for both tiles
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
+      umma_commit(&k_empty[0]);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nb; ++j) {
+        int s1 = s + 1;
+        uint32_t ph1 = ph;
+        if (s1 == A2_KS) {
+          s1 = 0;
+          ph1 ^= 1;
+        }
+        const bool more = (j + 1 < nb);
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          if (t == 0) mbar_wait(&v_full[s], ph);
+          tc_fence_after();
+          issue_pv(t, s, j != 0);
+          if (t == ntiles - 1) umma_commit(&v_empty[s]);
+          if (more) {
+            if (t == 0) {
+              mbar_wait(&k_full[s1], ph1);
+              tc_fence_after();
+            }
+            issue_s(t, s1);
+            if (t == ntiles - 1) umma_commit(&k_empty[s1]);
+          } else {
+            umma_commit(&o_full[t]);
+          }
+        }
+        s = s1;
+        ph = ph1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int t = (warp - 2) >> 2;  // tile
+    if (t == 0 || tileB_active) {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t tS = tmem_base + t * 128 + lane_base;
+      const uint32_t tO = tmem_base + 256 + t * 64 + lane_base;
+      uint8_t* p_row = sP + t * 2 * ATT_TILE + r * 128;
+      const int rx = r & 7;
+      const float sl2 = p.scale_log2;
+      float m_used = -INFINITY, l_run = 0.f;
+
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        const int valid = p.Nk - j * 128;
+        // pass 1: row max (two 32-column TMEM loads in flight per wait)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(tS + hlf * 64, va);
+          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
+          tmem_ld_wait();
+          if (valid < 128) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;  // -inf
+              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmax3(mx0, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(vb[e]), __uint_as_float(vb[e + 1]));
+          }
+        }
+        const float m_blk = fmaxf(mx0, mx1) * sl2;
+        if (j == 0) {
+          m_used = m_blk;
+        } else {
+          const bool need = m_blk > m_used + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? m_blk : m_used;
+            const float alpha = ex2_approx(m_used - m_new);
+            m_used = m_new;
+            l_run *= alpha;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld_32x32b_x32(tO + c * 32, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+              tmem_st_32x32b_x32(tO + c * 32, ov);
+            }
+            tmem_st_wait();
+          }
+        }
+        // pass 2: p = 2^(s*scale - m) -> fp16 P tile (A operand of the PV MMA), row sum
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(tS + hlf * 64, va);
+          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
+          tmem_ld_wait();
+          if (valid < 128) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;
+              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t* src = (g < 4) ? (va + g * 8) : (vb + (g - 4) * 8);
+            float pr[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pr[e] = ex2_approx(fmaf(__uint_as_float(src[e]), sl2, -m_used));
+            sum0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+            sum1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+            uint4 o;
+            o.x = pack_half2(pr[0], pr[1]);
+            o.y = pack_half2(pr[2], pr[3]);
+            o.z = pack_half2(pr[4], pr[5]);
+            o.w = pack_half2(pr[6], pr[7]);
+            // 16-byte chunk g of key half `hlf`, XOR-swizzled with the row (SWIZZLE_128B)
+            *reinterpret_cast<uint4*>(p_row + hlf * ATT_TILE + ((g ^ rx) << 4)) = o;
+          }
+        }
+        l_run += sum0 + sum1;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[t]);
+      }
+
+      // epilogue: O / l -> global
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      const int qrow = q0 + t * 128 + r;
+      const float inv = 1.f / l_run;
+      __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tO + c * 32, ov);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+            o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+            o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+            o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace ih
 
 using namespace ih;
@@ -339,7 +621,17 @@ extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, lon
   static bool configured = false;
   if (!configured) {
     IH_CUDA(cudaFuncSetAttribute(attn_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    IH_CUDA(cudaFuncSetAttribute(attn_f16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+    IH_CUDA(cudaFuncSetAttribute(attn2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
     configured = true;
+  }
+  if (n_ip == 0) {
+    dim3 grid2((Nq + 255) / 256, H, B);
+    attn2_f16_kernel<<<grid2, A2_THREADS, A2_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    IH_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
   }
   dim3 grid((Nq + 127) / 128, H, B);
   attn_f16_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);

@@ -2,8 +2,9 @@
 //
 //   out[M,N] = epilogue( A[M,K] * W[N,K]^T )           fp16 in, fp32 accumulate in TMEM, fp16 out
 //
-// One CTA computes one 128 x BN output tile. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single
-// thread tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> global). Operands are staged by TMA into
+// Persistent CTAs (one per SM) walk 128 x BN output tiles. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator
+// + single thread tcgen05.mma issuer, warps 2..9 = epilogue (TMEM -> registers -> global) overlapped with the next
+// tile's main loop through a double-buffered TMEM accumulator. Operands are staged by TMA into
 // 128B-swizzled shared memory (64 fp16 = one 128 B row per K-block), STAGES-deep mbarrier ring.
 //
 // Convolution is the same kernel ("im2col-free"): the activation is NHWC, the A tile of tap (dy,dx) is a 4-D TMA box
@@ -25,7 +26,6 @@ namespace ih {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 192;
 
 struct alignas(64) TmapSet4 {
   CUtensorMap m[4];
@@ -33,6 +33,7 @@ struct alignas(64) TmapSet4 {
 
 struct GemmParams {
   int M, N;     // logical output rows / cols (GEGLU: N = number of gated outputs)
+  int m_tiles;  // number of 128-row output tiles
   int num_kb;   // K blocks of 64 (taps * cin_kb for conv)
   int mode;     // 0 = plain GEMM, 1 = conv (4-D A maps)
   int cin_kb;   // conv: K blocks per tap
@@ -59,37 +60,33 @@ struct GemmSmem {
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS_P = (2 + GEMM_EPI_WARPS) * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The smem stage
+// ring runs continuously across tiles, and the fp32 accumulator is double-buffered in TMEM so that the epilogue of
+// tile i (TMEM -> registers -> global, 8 warps) overlaps the TMA/MMA main loop of tile i+1.
 template <int BN, int STAGES, bool GEGLU>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_constant__ TmapSet4 amaps,
-                                                                 const __grid_constant__ CUtensorMap bmap,
-                                                                 const GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __grid_constant__ TmapSet4 amaps,
+                                                                      const __grid_constant__ CUtensorMap bmap,
+                                                                      const GemmParams p) {
   using S = GemmSmem<BN, STAGES, GEGLU>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m_tile = blockIdx.y;
   constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
-  const int n0 = n_tile * BN_OUT;
-
-  // tile origin
-  int m0 = m_tile * BM;
-  int img = 0, x0 = 0, y0 = 0;
-  if (p.mode == 1) {
-    const int per_img = p.tiles_x * p.tiles_y;
-    img = m_tile / per_img;
-    const int t = m_tile - img * per_img;
-    y0 = (t / p.tiles_x) * p.bh;
-    x0 = (t % p.tiles_x) * p.bw;
-  }
+  const int n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
+  const int num_tiles = n_tiles * p.m_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&amaps.m[0]);
@@ -98,10 +95,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<(BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256)>(tmem_slot);
+  if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,28 +112,42 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sA = smem + stage * S::STAGE_BYTES;
-        uint8_t* sB = sA + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-        if (p.mode == 0) {
-          tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
-        } else {
-          const int tap = kb / p.cin_kb;
-          const int ckb = kb - tap * p.cin_kb;
-          tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
-                      y0 + p.tap_oy[tap], img);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % n_tiles;
+        const int m_tile = tile / n_tiles;
+        const int n0 = n_tile * BN_OUT;
+        const int m0 = m_tile * BM;
+        int img = 0, x0 = 0, y0 = 0;
+        if (p.mode == 1) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          img = m_tile / per_img;
+          const int t = m_tile - img * per_img;
+          y0 = (t / p.tiles_x) * p.bh;
+          x0 = (t % p.tiles_x) * p.bw;
         }
-        if (GEGLU) {
-          tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
-          tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
-        } else {
-          tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
-        }
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (p.mode == 0) {
+            tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
+          } else {
+            const int tap = kb / p.cin_kb;
+            const int ckb = kb - tap * p.cin_kb;
+            tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
+                        y0 + p.tap_oy[tap], img);
+          }
+          if (GEGLU) {
+            tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
+          } else {
+            tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -143,122 +157,154 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_con
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-        const uint64_t a_desc = umma_desc_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+            umma_f16_ss(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------ epilogue (8 warps) ------------------------
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp drains
     const int r = q * 32 + lane;
-    bool row_ok;
-    long long orow;
-    if (p.mode == 0) {
-      orow = (long long)m0 + r;
-      row_ok = orow < p.M;
-    } else {
-      const int hh = r / p.bw, ww = r - hh * p.bw;
-      const int y = y0 + hh, x = x0 + ww;
-      row_ok = (y < p.Ho) && (x < p.Wo) && (img * (long long)p.Ho * p.Wo < p.M);
-      orow = ((long long)img * p.Ho + y) * p.Wo + x;
-    }
-    const __half* rb = nullptr;
-    if (p.rowbias && row_ok) rb = p.rowbias + (orow / p.rows_per_group) * p.ld_rowbias;
+    constexpr int CHUNKS = BN_OUT / 32;   // 32-column chunks per tile
+    constexpr int CPW = (CHUNKS + 1) / 2; // chunks per warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % n_tiles;
+      const int m_tile = tile / n_tiles;
+      const int n0 = n_tile * BN_OUT;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      bool row_ok;
+      long long orow;
+      if (p.mode == 0) {
+        orow = (long long)m_tile * BM + r;
+        row_ok = orow < p.M;
+      } else {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = m_tile / per_img;
+        const int t = m_tile - img * per_img;
+        const int y0 = (t / p.tiles_x) * p.bh, x0 = (t % p.tiles_x) * p.bw;
+        const int hh = r / p.bw, ww = r - hh * p.bw;
+        const int y = y0 + hh, x = x0 + ww;
+        row_ok = (y < p.Ho) && (x < p.Wo);
+        orow = ((long long)img * p.Ho + y) * p.Wo + x;
+      }
+      const __half* rb = nullptr;
+      if (p.rowbias && row_ok) rb = p.rowbias + (orow / p.rows_per_group) * p.ld_rowbias;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-    for (int c = 0; c < BN_OUT / 32; ++c) {
-      const int col0 = n0 + c * 32;
-      if (col0 >= p.N) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + c * 32, v);
-      uint32_t g[32];
-      if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, g);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c = half * CPW + ci;
+        const int col0 = n0 + c * 32;
+        const bool live = (c < CHUNKS) && (col0 < p.N);   // warp-uniform
+        uint32_t v[32];
+        uint32_t g[32];
+        if (live) {
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, g);
+          tmem_ld_wait();
+        }
+        if (ci == CPW - 1) {
+          // all of this warp's TMEM reads of the accumulator are complete: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (live && row_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = col0 + j * 8;
-          if (col < p.N) {
-            float x[8];
+          for (int j = 0; j < 4; ++j) {
+            const int col = col0 + j * 8;
+            if (col < p.N) {
+              float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-            if (p.bias) {
-              const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + col);
-              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_half2(bw[e]);
-                x[2 * e] += f.x;
-                x[2 * e + 1] += f.y;
-              }
-            }
-            if (GEGLU) {
-              float gt[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j * 8 + e]);
+              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
               if (p.bias) {
-                const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col);
+                const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + col);
                 const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 f = unpack_half2(bw[e]);
-                  gt[2 * e] += f.x;
-                  gt[2 * e + 1] += f.y;
+                  x[2 * e] += f.x;
+                  x[2 * e + 1] += f.y;
                 }
               }
+              if (GEGLU) {
+                float gt[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
-            }
-            if (rb) {
-              const uint4 b4 = *reinterpret_cast<const uint4*>(rb + col);
-              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+                for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j * 8 + e]);
+                if (p.bias) {
+                  const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col);
+                  const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_half2(bw[e]);
-                x[2 * e] += f.x;
-                x[2 * e + 1] += f.y;
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_half2(bw[e]);
+                    gt[2 * e] += f.x;
+                    gt[2 * e + 1] += f.y;
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
               }
-            }
-            if (p.act == 1) {
+              if (rb) {
+                const uint4 b4 = *reinterpret_cast<const uint4*>(rb + col);
+                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
-            }
-            if (p.residual) {
-              const uint4 b4 = *reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
-              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_half2(bw[e]);
-                x[2 * e] += f.x;
-                x[2 * e + 1] += f.y;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_half2(bw[e]);
+                  x[2 * e] += f.x;
+                  x[2 * e + 1] += f.y;
+                }
               }
+              if (p.act == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
+              }
+              if (p.residual) {
+                const uint4 b4 = *reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_half2(bw[e]);
+                  x[2 * e] += f.x;
+                  x[2 * e + 1] += f.y;
+                }
+              }
+              uint4 o;
+              o.x = pack_half2(x[0], x[1]);
+              o.y = pack_half2(x[2], x[3]);
+              o.z = pack_half2(x[4], x[5]);
+              o.w = pack_half2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = o;
             }
-            uint4 o;
-            o.x = pack_half2(x[0], x[1]);
-            o.y = pack_half2(x[2], x[3]);
-            o.z = pack_half2(x[4], x[5]);
-            o.w = pack_half2(x[6], x[7]);
-            *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = o;
           }
         }
       }
@@ -267,14 +313,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f16_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<(BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256)>(tmem_base);
+  if (warp == 1) tmem_dealloc<S::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool GEGLU>
-static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, const GemmParams& p, int m_tiles,
+static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, GEGLU>;
   static bool configured = false;
@@ -284,28 +330,28 @@ static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, const Gem
     configured = true;
   }
   constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
-  dim3 grid((p.N + BN_OUT - 1) / BN_OUT, m_tiles, 1);
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(amaps, bmap, p);
+  p.m_tiles = m_tiles;
+  const long long tiles = (long long)((p.N + BN_OUT - 1) / BN_OUT) * m_tiles;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, GEMM_THREADS_P, S::TOTAL, stream>>>(amaps, bmap, p);
   IH_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-// crude cost model: waves * per-tile time; small BN tiles are shared-memory-bandwidth limited.
+// crude cost model for the persistent kernel (one CTA per SM): rounds of tiles * per-tile main-loop cost;
+// narrow tiles are shared-memory-bandwidth limited (A and B are re-read from smem for every MMA).
 static int pick_bn(long long m_tiles, int N) {
   const int sms = num_sms();
   double best = 1e30;
   int best_bn = 128;
   const int cands[3] = {256, 128, 64};
-  const double tile_cost[3] = {2.0, 1.0, 0.62};
-  const int occ[3] = {1, 2, 2};
+  const double tile_cost[3] = {2.0, 1.0, 0.75};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
-    const long long slots = (long long)sms * occ[i];
-    const long long waves = (tiles + slots - 1) / slots;
-    // two co-resident CTAs share one tensor pipe: a full wave of occ=2 costs occ * tile_cost
-    const double t = (double)waves * tile_cost[i] * occ[i] + 0.15 * waves;
+    const long long rounds = (tiles + sms - 1) / sms;
+    const double t = (double)rounds * tile_cost[i] + 0.1 * rounds;
     if (t < best - 1e-9) {
       best = t;
       best_bn = bn;
@@ -326,8 +372,8 @@ static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long lon
   if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, p, m_tiles, stream);
   switch (bn) {
     case 256: return launch_gemm<256, 4, false>(amaps, bmap, p, m_tiles, stream);
-    case 128: return launch_gemm<128, 3, false>(amaps, bmap, p, m_tiles, stream);
-    case 64: return launch_gemm<64, 4, false>(amaps, bmap, p, m_tiles, stream);
+    case 128: return launch_gemm<128, 6, false>(amaps, bmap, p, m_tiles, stream);
+    case 64: return launch_gemm<64, 8, false>(amaps, bmap, p, m_tiles, stream);
     default: return set_error(IH_ERR_ARG, "unsupported BN %d", bn);
   }
 }

@@ -31,17 +31,22 @@ __device__ __forceinline__ void store8(__half* p, const float (&x)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per (batch, group) sum and sum of squares, accumulated in double.
-// block = CV * R threads (CV = C/8 channel vectors, R row lanes); grid = (blocks_per_image, B).
+// GroupNorm statistics.  grid = (G row-chunks, B); block = CV * R threads (CV = C/8 channel vectors, R row lanes).
+// Each block writes fp32 partial (sum, sumsq) per group -- no atomics on the data path -- and the last block of an
+// image to finish (one atomic ticket per block) reduces the G partials in double and publishes mean / rstd.
+// workspace layout: [GN_MAXB] uint32 tickets at a FIXED offset (so calls with different B never scribble over them;
+// zero once, self-resetting) | floats: [B][GN_MAXG][2*groups] partials | [B][2*groups] mean,rstd
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int GN_MAXG = 128;
+constexpr int GN_MAXB = 1024;
+
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int groups, int R, double* __restrict__ stats) {
-  extern __shared__ float s_acc[];  // [2][C]
+                                int groups, int R, int rows_per_block, float eps, float* __restrict__ ws, int B) {
+  extern __shared__ float s_acc[];  // [R][2][C] per-row-lane partials (summed in a fixed order: deterministic)
+  __shared__ bool s_last;
   const int C = C0 + C1;
   const int CV = C >> 3;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   const int cv = threadIdx.x % CV;
   const int rl = threadIdx.x / CV;
   const int c = cv << 3;
@@ -57,7 +62,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-  for (int row = blockIdx.x * R + rl; row < HW; row += gridDim.x * R) {
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(HW, row_begin + rows_per_block);
+  int row = row_begin + rl;
+  for (; row + 3 * R < row_end; row += 4 * R) {  // 4 independent 16-byte loads in flight per thread
+    float v0[8], v1[8], v2[8], v3[8];
+    load8(src + (long long)row * stride, v0);
+    load8(src + (long long)(row + R) * stride, v1);
+    load8(src + (long long)(row + 2 * R) * stride, v2);
+    load8(src + (long long)(row + 3 * R) * stride, v3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+      q[e] += (v0[e] * v0[e] + v1[e] * v1[e]) + (v2[e] * v2[e] + v3[e] * v3[e]);
+    }
+  }
+  for (; row < row_end; row += R) {
     float v[8];
     load8(src + (long long)row * stride, v);
 #pragma unroll
@@ -66,42 +86,74 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
       q[e] += v[e] * v[e];
     }
   }
+  {
+    float* mine = s_acc + (long long)rl * 2 * C;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    atomicAdd(&s_acc[c + e], s[e]);
-    atomicAdd(&s_acc[C + c + e], q[e]);
+    for (int e = 0; e < 8; ++e) {
+      mine[c + e] = s[e];
+      mine[C + c + e] = q[e];
+    }
   }
   __syncthreads();
   const int cpg = C / groups;
+  float* part = ws + ((long long)b * GN_MAXG + blockIdx.x) * 2 * groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double ds = 0.0, dq = 0.0;
-    for (int i = 0; i < cpg; ++i) {
-      ds += (double)s_acc[g * cpg + i];
-      dq += (double)s_acc[C + g * cpg + i];
+    float ds = 0.f, dq = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      const float* pr = s_acc + (long long)rr * 2 * C;
+      for (int i = 0; i < cpg; ++i) {
+        ds += pr[g * cpg + i];
+        dq += pr[C + g * cpg + i];
+      }
     }
-    atomicAdd(&stats[((long long)b * groups + g) * 2 + 0], ds);
-    atomicAdd(&stats[((long long)b * groups + g) * 2 + 1], dq);
+    part[g] = ds;
+    part[groups + g] = dq;
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws) - GN_MAXB;  // ws points just past the ticket array
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[b], 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float* fin = ws + (long long)B * GN_MAXG * 2 * groups + (long long)b * 2 * groups;
+    const double n = (double)HW * cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      const volatile float* pp = ws + (long long)b * GN_MAXG * 2 * groups;
+      for (int k = 0; k < (int)gridDim.x; ++k) {
+        ds += (double)pp[(long long)k * 2 * groups + g];
+        dq += (double)pp[(long long)k * 2 * groups + groups + g];
+      }
+      const double mean = ds / n;
+      double var = dq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      fin[g] = (float)mean;
+      fin[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    if (threadIdx.x == 0) tickets[b] = 0u;  // self-reset for the next call
   }
 }
 
 __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int groups, int R, const double* __restrict__ stats, const __half* __restrict__ gamma,
-                                const __half* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
+                                int groups, int R, int rows_per_block, const float* __restrict__ fin_all,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta, int silu,
+                                __half* __restrict__ out) {
   extern __shared__ float s_ss[];  // scale[C], shift[C]
   const int C = C0 + C1;
   const int CV = C >> 3;
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  const double n = (double)HW * cpg;
+  const float* fin = fin_all + (long long)b * 2 * groups;
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g = ch / cpg;
-    const double mean = stats[((long long)b * groups + g) * 2 + 0] / n;
-    double var = stats[((long long)b * groups + g) * 2 + 1] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mean = fin[g], rstd = fin[groups + g];
     const float ga = __half2float(gamma[ch]), be = __half2float(beta[ch]);
     s_ss[ch] = ga * rstd;
-    s_ss[C + ch] = be - (float)mean * ga * rstd;
+    s_ss[C + ch] = be - mean * ga * rstd;
   }
   __syncthreads();
   const int cv = threadIdx.x % CV;
@@ -123,7 +175,25 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
     sh[e] = s_ss[C + c + e];
   }
   __half* dst = out + (long long)b * HW * C + c;
-  for (int row = blockIdx.x * R + rl; row < HW; row += gridDim.x * R) {
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(HW, row_begin + rows_per_block);
+  int row = row_begin + rl;
+  for (; row + 3 * R < row_end; row += 4 * R) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(src + (long long)(row + u * R) * stride, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = v[u][e] * sc[e] + sh[e];
+        if (silu) y = silu_f(y);
+        v[u][e] = y;
+      }
+      store8(dst + (long long)(row + u * R) * C, v[u]);
+    }
+  }
+  for (; row < row_end; row += R) {
     float v[8];
     load8(src + (long long)row * stride, v);
 #pragma unroll
@@ -137,65 +207,67 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, values held in registers (two-pass mean / variance), C <= 8 * 32 * LN_MAXV.
+// LayerNorm: one 16-byte vector per thread, TPR (multiple of 32) threads per row, several rows per block.
+// two-pass (mean, then centred variance) in registers.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 16;  // C up to 4096
-
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
-                                 const __half* __restrict__ beta, __half* __restrict__ out, int rows, int C,
+                                 const __half* __restrict__ beta, __half* __restrict__ out, int rows, int C, int TPR,
                                  float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  __shared__ float s_red[2][32];
+  const int rpb = blockDim.x / TPR;
+  const int rl = threadIdx.x / TPR;
+  const int tr = threadIdx.x - rl * TPR;
+  const int row = blockIdx.x * rpb + rl;
   const int CV = C >> 3;
-  const __half* src = x + (long long)warp * C;
-  float v[LN_MAXV][8];
-  float sum = 0.f;
+  const bool active = (row < rows) && (tr < CV);
+  const int wpr = TPR >> 5;                 // warps per row
+  const int wrow = (threadIdx.x >> 5);      // this thread's warp index in the block
+  const int w0 = rl * wpr;                  // first warp of this row
+  float v[8];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
-      load8(src + cv * 8, v[i]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[i][e];
-    }
-  }
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (active) load8(x + (long long)row * C + tr * 8, v);
+  float sum = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
+  if ((threadIdx.x & 31) == 0) s_red[0][wrow] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < wpr; ++w) tot += s_red[0][w0 + w];
+  const float mean = tot / (float)C;
   float sq = 0.f;
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = v[i][e] - mean;
-        sq += d * d;
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float d = v[e] - mean;
+      sq += d * d;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)C + eps);
-  __half* dst = out + (long long)warp * C;
+  if ((threadIdx.x & 31) == 0) s_red[1][wrow] = sq;
+  __syncthreads();
+  float tq = 0.f;
+  for (int w = 0; w < wpr; ++w) tq += s_red[1][w0 + w];
+  const float rstd = rsqrtf(tq / (float)C + eps);
+  if (active) {
+    float g[8], bt[8], y[8];
+    load8(gamma + tr * 8, g);
+    load8(beta + tr * 8, bt);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
-      float g[8], bt[8], y[8];
-      load8(gamma + cv * 8, g);
-      load8(beta + cv * 8, bt);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd * g[e] + bt[e];
-      store8(dst + cv * 8, y);
-    }
+    for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd * g[e] + bt[e];
+    store8(out + (long long)row * C + tr * 8, y);
   }
 }
 
 }  // namespace ih
 
 using namespace ih;
+
+extern "C" long long ih_groupnorm_workspace_bytes(int B, int groups) {
+  return ((long long)B * GN_MAXG * 2 * groups + (long long)B * 2 * groups) * (long long)sizeof(float) +
+         (long long)GN_MAXB * (long long)sizeof(unsigned int);
+}
 
 extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void* gamma, const void* beta,
                                 void* out, void* stats_ws, int B, int HW, int groups, float eps, int silu,
@@ -208,22 +280,26 @@ extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, 
            "ih_groupnorm_f16: C0=%d C1=%d groups=%d unsupported", C0, C1, groups);
   const int CV = C / 8;
   IH_CHECK(CV <= 1024, IH_ERR_SHAPE, "ih_groupnorm_f16: C too large");
+  IH_CHECK(B <= GN_MAXB, IH_ERR_SHAPE, "ih_groupnorm_f16: B=%d exceeds %d", B, GN_MAXB);
   int R = 256 / CV;
   if (R < 1) R = 1;
   const int threads = CV * R;
-  int blocks = (HW + R - 1) / R;
-  const int cap = (num_sms() * 4 + B - 1) / B;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  IH_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * groups, stream));
-  dim3 grid(blocks, B);
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>((const __half*)x0, C0, (const __half*)x1, C1, HW,
-                                                                     groups, R, (double*)stats_ws);
+  // row chunks per image: about two blocks per SM overall, at most GN_MAXG per image
+  int G = (2 * num_sms() + B - 1) / B;
+  if (G > GN_MAXG) G = GN_MAXG;
+  int rows_per_block = (HW + G - 1) / G;
+  if (rows_per_block < 4 * R) rows_per_block = 4 * R;
+  G = (HW + rows_per_block - 1) / rows_per_block;
+  dim3 grid(G, B);
+  float* ws = (float*)((unsigned int*)stats_ws + GN_MAXB);
+  gn_stats_kernel<<<grid, threads, (size_t)R * 2 * C * sizeof(float), stream>>>((const __half*)x0, C0, (const __half*)x1, C1, HW,
+                                                                     groups, R, rows_per_block, eps, ws, B);
   IH_CUDA(cudaGetLastError());
+  const float* fin = ws + (long long)B * GN_MAXG * 2 * groups;
   gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>((const __half*)x0, C0, (const __half*)x1, C1, HW,
-                                                                     groups, R, (const double*)stats_ws,
-                                                                     (const __half*)gamma, (const __half*)beta, eps,
-                                                                     silu, (__half*)out);
+                                                                     groups, R, rows_per_block, fin,
+                                                                     (const __half*)gamma, (const __half*)beta, silu,
+                                                                     (__half*)out);
   IH_CUDA(cudaGetLastError());
   count_launch(2);
   return 0;
@@ -232,11 +308,14 @@ extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, 
 extern "C" int ih_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int C,
                                 float eps, void* stream) {
   IH_CHECK(x && gamma && beta && out, IH_ERR_ARG, "ih_layernorm_f16: null pointer");
-  IH_CHECK(C % 8 == 0 && C <= 8 * 32 * LN_MAXV && rows > 0, IH_ERR_SHAPE, "ih_layernorm_f16: C=%d unsupported", C);
-  const int warps_per_block = 8;
-  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, C, eps);
+  IH_CHECK(C % 8 == 0 && C <= 8 * 1024 && rows > 0, IH_ERR_SHAPE, "ih_layernorm_f16: C=%d unsupported", C);
+  const int CV = C / 8;
+  const int TPR = ((CV + 31) / 32) * 32;
+  int rpb = 256 / TPR;
+  if (rpb < 1) rpb = 1;
+  const int blocks = (rows + rpb - 1) / rpb;
+  layernorm_kernel<<<blocks, TPR * rpb, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)gamma,
+                                                                   (const __half*)beta, (__half*)out, rows, C, TPR, eps);
   IH_CUDA(cudaGetLastError());
   count_launch();
   return 0;

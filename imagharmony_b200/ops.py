@@ -111,6 +111,21 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int,
     return out
 
 
+_gn_ws = {}
+
+
+def _gn_workspace(device, B: int, groups: int) -> torch.Tensor:
+    """Persistent zero-initialised statistics workspace (one per device; GroupNorm calls are stream-ordered)."""
+    need = int(_lib.load().ih_groupnorm_workspace_bytes(B, groups))
+    ws = _gn_ws.get(device)
+    if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise IHError("groupnorm workspace must be created before CUDA-graph capture (run one warm-up step)")
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _gn_ws[device] = ws
+    return ws
+
+
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None,
               groups: int = 32, eps: float = 1e-5, silu: bool = False, out: Optional[torch.Tensor] = None,
               ws: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -123,8 +138,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: 
         raise IHError("groupnorm: inputs must be contiguous NHWC")
     if out is None:
         out = torch.empty((B, H, W, C0 + C1), dtype=torch.float16, device=x0.device)
-    if ws is None:   # tiny per-call statistics workspace (comes from the graph's private pool under capture)
-        ws = torch.empty(2 * B * groups, dtype=torch.float64, device=x0.device)
+    if ws is None:
+        ws = _gn_workspace(x0.device, B, groups)
     rc = lib.ih_groupnorm_f16(x0.data_ptr(), C0, _p(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
                               ws.data_ptr(), B, H * W, groups, float(eps), int(silu), _stream())
     check(rc, "ih_groupnorm_f16")

@@ -57,8 +57,10 @@ int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk,
                      void* stream);
 
 /* GroupNorm over NHWC [B, HW, C] (optionally the channel-concatenation of two tensors x0 [.., C0] and x1 [.., C1]),
- * fp32 statistics, optional fused SiLU.  stats workspace: 2*B*groups doubles (zeroed by the call).
- * Replaces nn.GroupNorm (+ nn.SiLU) in diffusers ResnetBlock2D / Transformer2DModel. */
+ * fp32 partial sums reduced in double, optional fused SiLU.  stats_ws: ih_groupnorm_workspace_bytes(B, groups) bytes,
+ * zero-initialised ONCE by the caller (the kernels leave its ticket counters at zero again) and not shared by
+ * concurrently running calls.  Replaces nn.GroupNorm (+ nn.SiLU) in diffusers ResnetBlock2D / Transformer2DModel. */
+long long ih_groupnorm_workspace_bytes(int B, int groups);
 int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void* gamma, const void* beta, void* out,
                      void* stats_ws, int B, int HW, int groups, float eps, int silu, void* stream);
 

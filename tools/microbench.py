@@ -12,16 +12,23 @@ from imagharmony_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    """GPU time per call: `iters` calls captured into one CUDA graph (no host launch overhead), replayed 3x."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(3):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e-3
+    return s.elapsed_time(e) / (3 * iters) * 1e-3
 
 
 def r(*shape, scale=1.0):
