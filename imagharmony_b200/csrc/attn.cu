@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_f16_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_S = tmem_base;        // 128 columns
   const uint32_t tmem_O = tmem_base + 128;  // 64 columns
 
@@ -357,6 +359,8 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -628,14 +632,10 @@ extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, lon
   }
   if (n_ip == 0) {
     dim3 grid2((Nq + 255) / 256, H, B);
-    attn2_f16_kernel<<<grid2, A2_THREADS, A2_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    IH_CUDA(cudaGetLastError());
-    count_launch();
+    IH_CUDA(launch_kernel(attn2_f16_kernel, dim3(grid2), dim3(A2_THREADS), (size_t)(A2_SMEM_BYTES), (cudaStream_t)stream, tq, tk, tv, p));
     return 0;
   }
   dim3 grid((Nq + 127) / 128, H, B);
-  attn_f16_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(attn_f16_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)(ATT_SMEM_BYTES), (cudaStream_t)stream, tq, tk, tv, p));
   return 0;
 }

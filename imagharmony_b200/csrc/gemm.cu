@@ -50,7 +50,7 @@ struct GemmParams {
   long long ldr;
   __half* out;
   long long ldo;
-  int act;  // 0 none, 1 SiLU (applied after bias, before residual)
+  int act;  // 0 none, 1 SiLU, 2 GELU(erf) (applied after bias, before residual)
 };
 
 template <int BN, int STAGES, bool GEGLU>
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel may begin its prologue now ...
+  pdl_wait();               // ... and we may not touch global memory before our predecessor has finished
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -287,6 +289,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               if (p.act == 1) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
+              } else if (p.act == 2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
               }
               if (p.residual) {
                 const uint4 b4 = *reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
@@ -333,25 +338,27 @@ static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, GemmParam
   p.m_tiles = m_tiles;
   const long long tiles = (long long)((p.N + BN_OUT - 1) / BN_OUT) * m_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  kern<<<grid, GEMM_THREADS_P, S::TOTAL, stream>>>(amaps, bmap, p);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, amaps, bmap, p));
   return 0;
 }
 
-// crude cost model for the persistent kernel (one CTA per SM): rounds of tiles * per-tile main-loop cost;
-// narrow tiles are shared-memory-bandwidth limited (A and B are re-read from smem for every MMA).
+// Cost model for the persistent kernel (one CTA per SM), calibrated on B200 (tools/microbench.py):
+//   * a 128x256 tile streams 48 KiB of operands per 2^22 MACs; a 128x128 tile 32 KiB per 2^21 MACs -- the narrower
+//     tile needs 1.33x the L2->SM bytes per FLOP and is latency/L2-bound (785 vs 1180 TFLOP/s at 8192^3), so its cost
+//     per tile is ~0.75 of the wide tile, not 0.5; 128x64 tiles are worse still and only used for N <= 64.
+//   * padded columns of a partially filled last N tile cost as much as real ones.
 static int pick_bn(long long m_tiles, int N) {
+  if (N <= 64) return 64;
   const int sms = num_sms();
   double best = 1e30;
-  int best_bn = 128;
-  const int cands[3] = {256, 128, 64};
-  const double tile_cost[3] = {2.0, 1.0, 0.75};
-  for (int i = 0; i < 3; ++i) {
+  int best_bn = 256;
+  const int cands[2] = {256, 128};
+  const double tile_cost[2] = {2.0, 1.5};
+  for (int i = 0; i < 2; ++i) {
     const int bn = cands[i];
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
     const long long rounds = (tiles + sms - 1) / sms;
-    const double t = (double)rounds * tile_cost[i] + 0.1 * rounds;
+    const double t = (double)rounds * (tile_cost[i] + 0.15);
     if (t < best - 1e-9) {
       best = t;
       best_bn = bn;
@@ -417,7 +424,7 @@ extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const vo
   p.ldr = ldr;
   p.out = (__half*)out;
   p.ldo = ldo;
-  p.act = (epilogue & IH_EPI_SILU) ? 1 : 0;
+  p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : 0);
   const int m_tiles = (M + BM - 1) / BM;
   return dispatch(amaps, w, N, K, p, m_tiles, geglu, tile_n, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -108,6 +109,14 @@ int num_sms() {
     return v > 0 ? v : 148;
   }();
   return n;
+}
+
+bool pdl_enabled() {
+  static bool on = [] {
+    const char* e = getenv("IH_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -31,4 +31,27 @@ int num_sms();
 // launch counter (all kernels launched by this library since the last reset) -- bench.py's "gpu_launches"
 void count_launch(int n = 1);
 
+// Programmatic dependent launch (PDL): every kernel of this library executes griddepcontrol.wait before it touches
+// global memory, so consecutive launches may overlap the next kernel's prologue (barrier init, TMEM allocation,
+// descriptor prefetch, CTA scheduling) with the previous kernel's tail.  IH_PDL=0 in the environment disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+
 }  // namespace ih

@@ -44,6 +44,8 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
                                 int groups, int R, int rows_per_block, float eps, float* __restrict__ ws, int B) {
   extern __shared__ float s_acc[];  // [R][2][C] per-row-lane partials (summed in a fixed order: deterministic)
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = C0 + C1;
   const int CV = C >> 3;
   const int b = blockIdx.y;
@@ -119,14 +121,30 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
   __syncthreads();
   if (s_last) {
     __threadfence();
-    float* fin = ws + (long long)B * GN_MAXG * 2 * groups + (long long)b * 2 * groups;
+    // all threads reduce the G partials: value index v = t % (2*groups), slice = t / (2*groups); L2 (ld.cg) loads
+    // are independent so they pipeline; fixed summation order keeps the result deterministic.
+    double* s_red = reinterpret_cast<double*>(s_acc);  // reuse (>= 2*C floats >= 2*groups*slices doubles)
+    const int nv = 2 * groups;
+    int slices = blockDim.x / nv;
+    if (slices < 1) slices = 1;
+    if (slices > 4) slices = 4;
+    const float* pp = ws + (long long)b * GN_MAXG * nv;
+    __syncthreads();
+    if ((int)threadIdx.x < nv * slices) {
+      const int v = threadIdx.x % nv, sl = threadIdx.x / nv;
+      double a = 0.0;
+#pragma unroll 8
+      for (int k = sl; k < (int)gridDim.x; k += slices) a += (double)__ldcg(pp + (long long)k * nv + v);
+      s_red[sl * nv + v] = a;
+    }
+    __syncthreads();
+    float* fin = ws + (long long)B * GN_MAXG * nv + (long long)b * nv;
     const double n = (double)HW * cpg;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       double ds = 0.0, dq = 0.0;
-      const volatile float* pp = ws + (long long)b * GN_MAXG * 2 * groups;
-      for (int k = 0; k < (int)gridDim.x; ++k) {
-        ds += (double)pp[(long long)k * 2 * groups + g];
-        dq += (double)pp[(long long)k * 2 * groups + groups + g];
+      for (int sl = 0; sl < slices; ++sl) {
+        ds += s_red[sl * nv + g];
+        dq += s_red[sl * nv + groups + g];
       }
       const double mean = ds / n;
       double var = dq / n - mean * mean;
@@ -143,6 +161,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, int silu,
                                 __half* __restrict__ out) {
   extern __shared__ float s_ss[];  // scale[C], shift[C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = C0 + C1;
   const int CV = C >> 3;
   const int b = blockIdx.y;
@@ -214,6 +234,8 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
                                  const __half* __restrict__ beta, __half* __restrict__ out, int rows, int C, int TPR,
                                  float eps) {
   __shared__ float s_red[2][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int rpb = blockDim.x / TPR;
   const int rl = threadIdx.x / TPR;
   const int tr = threadIdx.x - rl * TPR;
@@ -292,16 +314,13 @@ extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, 
   G = (HW + rows_per_block - 1) / rows_per_block;
   dim3 grid(G, B);
   float* ws = (float*)((unsigned int*)stats_ws + GN_MAXB);
-  gn_stats_kernel<<<grid, threads, (size_t)R * 2 * C * sizeof(float), stream>>>((const __half*)x0, C0, (const __half*)x1, C1, HW,
-                                                                     groups, R, rows_per_block, eps, ws, B);
-  IH_CUDA(cudaGetLastError());
+  IH_CUDA(launch_kernel(gn_stats_kernel, dim3(grid), dim3(threads), (size_t)((size_t)R * 2 * C * sizeof(float)), stream, (const __half*)x0, C0, (const __half*)x1, C1, HW,
+                                                                     groups, R, rows_per_block, eps, ws, B));
   const float* fin = ws + (long long)B * GN_MAXG * 2 * groups;
-  gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>((const __half*)x0, C0, (const __half*)x1, C1, HW,
+  IH_CUDA(launch_kernel(gn_apply_kernel, dim3(grid), dim3(threads), (size_t)(2 * C * sizeof(float)), stream, (const __half*)x0, C0, (const __half*)x1, C1, HW,
                                                                      groups, R, rows_per_block, fin,
                                                                      (const __half*)gamma, (const __half*)beta, silu,
-                                                                     (__half*)out);
-  IH_CUDA(cudaGetLastError());
-  count_launch(2);
+                                                                     (__half*)out));
   return 0;
 }
 
@@ -314,9 +333,7 @@ extern "C" int ih_layernorm_f16(const void* x, const void* gamma, const void* be
   int rpb = 256 / TPR;
   if (rpb < 1) rpb = 1;
   const int blocks = (rows + rpb - 1) / rpb;
-  layernorm_kernel<<<blocks, TPR * rpb, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)gamma,
-                                                                   (const __half*)beta, (__half*)out, rows, C, TPR, eps);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(layernorm_kernel, dim3(blocks), dim3(TPR * rpb), (size_t)(0), (cudaStream_t)stream, (const __half*)x, (const __half*)gamma,
+                                                                   (const __half*)beta, (__half*)out, rows, C, TPR, eps));
   return 0;
 }

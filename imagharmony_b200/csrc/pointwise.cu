@@ -29,7 +29,9 @@ constexpr int SL_MAXM = 8;
 __global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ w,
                                     const __half* __restrict__ bias, const __half* __restrict__ addend,
                                     long long ld_add, __half* __restrict__ out, long long ldo, int M, int N, int K,
-                                    int act_in, int act_out) {
+                                    int act_in, int act_out, float out_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -64,6 +66,7 @@ __global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx,
     for (int m = 0; m < M; ++m) {
       float y = __half2float(__float2half_rn(acc[m] + b));  // nn.Linear output is fp16 before the activation
       if (act_out == 1) y = silu_f(y);
+      if (out_scale != 1.f) y = __half2float(__float2half_rn(y)) * out_scale;  // `module(x) * scale` on an fp16 tensor
       if (addend) y = __half2float(__float2half_rn(y)) + __half2float(addend[m * ld_add + n]);  // fp16 tensor add
       out[m * ldo + n] = __float2half_rn(y);
     }
@@ -75,6 +78,8 @@ __global__ void linear_small_kernel(const __half* __restrict__ x, long long ldx,
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void sinusoid_kernel(const float* __restrict__ t, const int* __restrict__ step, __half* __restrict__ out,
                                 long long ldo, int n, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half_dim = dim >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * half_dim) return;
@@ -87,6 +92,8 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, const int* __restri
 }
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * 2 * H * 2 * W * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -101,6 +108,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 
 __global__ void concat_kernel(const uint4* __restrict__ x0, int CV0, const uint4* __restrict__ x1, int CV1,
                               uint4* __restrict__ out, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = CV0 + CV1;
   const long long total = rows * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -116,6 +125,8 @@ __global__ void concat_kernel(const uint4* __restrict__ x0, int CV0, const uint4
 __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                const __half* __restrict__ bias, __half* __restrict__ out, int B, int H, int W, int Cin,
                                int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __half s_w[];  // [Cin*9][Cout]
   const int K = Cin * 9;
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -165,6 +176,8 @@ constexpr int CO_MAX = 8;
 __global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                 const __half* __restrict__ bias, __half* __restrict__ out, int B, int H, int W, int Cin,
                                 int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __half s_w[];  // [Cout][9][Cin]
   for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) {
     const int o = i / (9 * Cin);
@@ -224,6 +237,8 @@ __global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __re
 __global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __restrict__ latents,
                                  __half* __restrict__ model_in, const float* __restrict__ sigmas,
                                  const int* __restrict__ step, float guidance, long long per_image, int n_images) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = *step;
   const float sigma = sigmas[i], sigma_next = sigmas[i + 1];
   const float den_next = sqrtf(sigma_next * sigma_next + 1.f);
@@ -248,11 +263,17 @@ __global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __res
     model_in[total + idx] = mi;
   }
 }
-__global__ void step_inc_kernel(int* step) { *step += 1; }
+__global__ void step_inc_kernel(int* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step += 1;
+}
 
 __global__ void scale_model_input_kernel(const __half* __restrict__ latents, __half* __restrict__ model_in,
                                          const float* __restrict__ sigmas, const int* __restrict__ step,
                                          long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sigma = sigmas[*step];
   const float den = sqrtf(sigma * sigma + 1.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -260,6 +281,59 @@ __global__ void scale_model_input_kernel(const __half* __restrict__ latents, __h
     const __half mi = __float2half_rn(__half2float(latents[idx]) / den);
     model_in[idx] = mi;
     model_in[total + idx] = mi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small generic attention (any head dims <= 128, few queries): one warp per (batch, head, query).
+// HarmonyAttention's Cross_Attention (attention_processor.py:35-56): head_dim 40, value dim 64; scores are DIVIDED by
+// `scale` = sqrt(head_dim) exactly like the reference (:45).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SA_MAXK = 1024;
+__global__ void attention_small_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k,
+                                       long long ldk, const __half* __restrict__ v, long long ldv,
+                                       __half* __restrict__ out, long long ldo, int H, int Nq, int Nk, int dqk, int dv,
+                                       float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_p[];  // [warps][Nk]
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_block;  // (b, h, iq)
+  const int iq = gw % Nq;
+  const int h = (gw / Nq) % H;
+  const int b = gw / (Nq * H);
+  float* p = s_p + warp_in_block * Nk;
+  const __half* qr = q + ((long long)b * Nq + iq) * ldq + h * dqk;
+  float mx = -INFINITY;
+  for (int j = lane; j < Nk; j += 32) {
+    const __half* kr = k + ((long long)b * Nk + j) * ldk + h * dqk;
+    float acc = 0.f;
+    for (int d = 0; d < dqk; ++d) acc += __half2float(qr[d]) * __half2float(kr[d]);
+    // the reference rounds the fp16 matmul output before dividing by the scale (attention_processor.py:45)
+    acc = __half2float(__float2half_rn(__half2float(__float2half_rn(acc)) / scale));
+    p[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < Nk; j += 32) {
+    const float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  for (int d = lane; d < dv; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < Nk; ++j) {
+      const float pj = __half2float(__float2half_rn(p[j] * inv));  // softmax output is an fp16 tensor
+      acc += pj * __half2float(v[((long long)b * Nk + j) * ldv + h * dv + d]);
+    }
+    out[((long long)b * Nq + iq) * ldo + h * dv + d] = __float2half_rn(acc);
   }
 }
 
@@ -277,19 +351,17 @@ using namespace ih;
 
 extern "C" int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, const void* addend,
                                    long long ld_add, void* out, long long ldo, int M, int N, int K, int act_in,
-                                   int act_out, void* stream) {
+                                   int act_out, float out_scale, void* stream) {
   IH_CHECK(x && w && out, IH_ERR_ARG, "ih_linear_small_f16: null pointer");
   IH_CHECK(M >= 1 && M <= 64, IH_ERR_SHAPE, "ih_linear_small_f16: M=%d must be in [1,64] (use ih_gemm_f16)", M);
   IH_CHECK(K % 8 == 0 && ldx % 8 == 0, IH_ERR_ALIGN, "ih_linear_small_f16: K and ldx must be multiples of 8");
   const int warps = 8;
   for (int m0 = 0; m0 < M; m0 += SL_MAXM) {  // row chunks of 8 (W is re-read from L2 for the later chunks)
     const int mc = (M - m0) < SL_MAXM ? (M - m0) : SL_MAXM;
-    linear_small_kernel<<<(N + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+    IH_CUDA(launch_kernel(linear_small_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), (size_t)(0), (cudaStream_t)stream, 
         (const __half*)x + m0 * ldx, ldx, (const __half*)w, (const __half*)bias,
         addend ? (const __half*)addend + m0 * ld_add : nullptr, ld_add, (__half*)out + m0 * ldo, ldo, mc, N, K,
-        act_in, act_out);
-    IH_CUDA(cudaGetLastError());
-    count_launch();
+        act_in, act_out, out_scale));
   }
   return 0;
 }
@@ -298,30 +370,24 @@ extern "C" int ih_sinusoid_f16(const void* t_f32, const void* step_i32, void* ou
                                void* stream) {
   IH_CHECK(t_f32 && out && dim % 2 == 0, IH_ERR_ARG, "ih_sinusoid_f16: bad arguments");
   const int total = n * (dim / 2);
-  sinusoid_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)t_f32, (const int*)step_i32,
-                                                                         (__half*)out, ldo, n, dim);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(sinusoid_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)t_f32, (const int*)step_i32,
+                                                                         (__half*)out, ldo, n, dim));
   return 0;
 }
 
 extern "C" int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream) {
   IH_CHECK(x && out && C % 8 == 0, IH_ERR_ARG, "ih_upsample2x_f16: bad arguments");
   const long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W,
-                                                                            C / 8);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const uint4*)x, (uint4*)out, B, H, W,
+                                                                            C / 8));
   return 0;
 }
 
 extern "C" int ih_concat_f16(const void* x0, int C0, const void* x1, int C1, void* out, long long rows, void* stream) {
   IH_CHECK(x0 && x1 && out && C0 % 8 == 0 && C1 % 8 == 0, IH_ERR_ARG, "ih_concat_f16: bad arguments");
   const long long total = rows * ((C0 + C1) / 8);
-  concat_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x0, C0 / 8, (const uint4*)x1,
-                                                                        C1 / 8, (uint4*)out, rows);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(concat_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const uint4*)x0, C0 / 8, (const uint4*)x1,
+                                                                        C1 / 8, (uint4*)out, rows));
   return 0;
 }
 
@@ -330,10 +396,8 @@ extern "C" int ih_conv_in_f16(const void* x_nchw, const void* w, const void* bia
   IH_CHECK(x_nchw && w && out, IH_ERR_ARG, "ih_conv_in_f16: null pointer");
   IH_CHECK(Cin <= 8 && Cout % 8 == 0 && Cin * 9 * Cout * 2 <= 48 * 1024, IH_ERR_SHAPE, "ih_conv_in_f16: bad shape");
   const long long total = (long long)B * H * W * (Cout / 8);
-  conv_in_kernel<<<grid_for(total, 256), 256, Cin * 9 * Cout * 2, (cudaStream_t)stream>>>(
-      (const __half*)x_nchw, (const __half*)w, (const __half*)bias, (__half*)out, B, H, W, Cin, Cout);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(conv_in_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(Cin * 9 * Cout * 2), (cudaStream_t)stream, 
+      (const __half*)x_nchw, (const __half*)w, (const __half*)bias, (__half*)out, B, H, W, Cin, Cout));
   return 0;
 }
 
@@ -346,10 +410,8 @@ extern "C" int ih_conv_out_f16(const void* x, const void* w, const void* bias, v
   long long blocks = (npix + 7) / 8;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  conv_out_kernel<<<(int)blocks, 256, Cout * 9 * Cin * 2, (cudaStream_t)stream>>>(
-      (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)out_nchw, B, H, W, Cin, Cout);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(conv_out_kernel, dim3((int)blocks), dim3(256), (size_t)(Cout * 9 * Cin * 2), (cudaStream_t)stream, 
+      (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)out_nchw, B, H, W, Cin, Cout));
   return 0;
 }
 
@@ -358,22 +420,36 @@ extern "C" int ih_euler_cfg_step(const void* noise_pred, void* latents, void* mo
   cudaStream_t stream = (cudaStream_t)stream_;
   IH_CHECK(noise_pred && latents && model_in && sigmas && step, IH_ERR_ARG, "ih_euler_cfg_step: null pointer");
   const long long total = n_per_image * n_images;
-  euler_cfg_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const __half*)noise_pred, (__half*)latents,
+  IH_CUDA(launch_kernel(euler_cfg_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, (const __half*)noise_pred, (__half*)latents,
                                                              (__half*)model_in, (const float*)sigmas,
-                                                             (const int*)step, guidance, n_per_image, n_images);
-  IH_CUDA(cudaGetLastError());
-  step_inc_kernel<<<1, 1, 0, stream>>>((int*)step);
-  IH_CUDA(cudaGetLastError());
-  count_launch(2);
+                                                             (const int*)step, guidance, n_per_image, n_images));
+  IH_CUDA(launch_kernel(step_inc_kernel, dim3(1), dim3(1), (size_t)(0), stream, (int*)step));
   return 0;
 }
 
 extern "C" int ih_scale_model_input(const void* latents, void* model_in, const void* sigmas, const void* step,
                                     long long total, void* stream) {
   IH_CHECK(latents && model_in && sigmas && step, IH_ERR_ARG, "ih_scale_model_input: null pointer");
-  scale_model_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, total);
-  IH_CUDA(cudaGetLastError());
-  count_launch();
+  IH_CUDA(launch_kernel(scale_model_input_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+      (const __half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, total));
+  return 0;
+}
+
+extern "C" int ih_attention_small_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                      long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk, int dqk,
+                                      int dv, float scale, void* stream) {
+  IH_CHECK(q && k && v && out, IH_ERR_ARG, "ih_attention_small_f16: null pointer");
+  IH_CHECK(Nk >= 1 && Nk <= SA_MAXK && dqk >= 1 && dqk <= 128 && dv >= 1 && dv <= 128 && Nq >= 1, IH_ERR_SHAPE,
+           "ih_attention_small_f16: Nk<=%d, head dims <= 128 required", SA_MAXK);
+  const int warps = 4;
+  const long long total = (long long)B * H * Nq;
+  IH_CHECK(total % warps == 0 || true, IH_ERR_SHAPE, "unreachable");
+  const int blocks = (int)((total + warps - 1) / warps);
+  // pad the grid so every warp index is valid: the kernel indexes (b,h,iq) from the global warp id
+  IH_CHECK(total == (long long)blocks * warps, IH_ERR_SHAPE,
+           "ih_attention_small_f16: B*H*Nq = %lld must be a multiple of %d", total, warps);
+  IH_CUDA(launch_kernel(attention_small_kernel, dim3(blocks), dim3(warps * 32), (size_t)(warps * Nk * sizeof(float)), (cudaStream_t)stream, 
+      (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo, H, Nq, Nk, dqk, dv,
+      scale));
   return 0;
 }

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import IHError, check
 
-EPI_NONE, EPI_GEGLU, EPI_SILU = 0, 1, 2
+EPI_NONE, EPI_GEGLU, EPI_SILU, EPI_GELU = 0, 1, 2, 4
 
 
 def _stream() -> int:
@@ -48,7 +48,7 @@ def launch_count_reset() -> None:
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
-           rows_per_group: int = 0, geglu: bool = False, silu: bool = False,
+           rows_per_group: int = 0, geglu: bool = False, silu: bool = False, gelu: bool = False,
            out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
     """out = epi(x @ w.T + bias + rowbias[row // rows_per_group]) + residual ; x [M,K], w [N,K] (nn.Linear layout)."""
     lib = _lib.load()
@@ -62,7 +62,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
     ldr = _rows(residual, "residual") if residual is not None else 0
     ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
-    epi = (EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0)
+    epi = (EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0) | (EPI_GELU if gelu else 0)
     rc = lib.ih_gemm_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(rowbias), rows_per_group, ldrb,
                          _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _stream())
     check(rc, "ih_gemm_f16")
@@ -163,7 +163,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act_in: bool = False,
-                 act_out: bool = False, addend: Optional[torch.Tensor] = None,
+                 act_out: bool = False, addend: Optional[torch.Tensor] = None, out_scale: float = 1.0,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Small-M (<= 8 rows) linear with optional SiLU on the input and/or output and an optional fp16 addend."""
     lib = _lib.load()
@@ -176,8 +176,23 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
         raise IHError(f"linear_small: M={M} > 64 rows; use ops.linear")
     ld_add = _rows(addend, "addend") if addend is not None else 0
     rc = lib.ih_linear_small_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(addend), ld_add,
-                                 out.data_ptr(), _rows(out, "out"), M, N, K, int(act_in), int(act_out), _stream())
+                                 out.data_ptr(), _rows(out, "out"), M, N, K, int(act_in), int(act_out),
+                                 float(out_scale), _stream())
     check(rc, "ih_linear_small_f16")
+    return out
+
+
+def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Nq: int, Nk: int, dqk: int,
+                    dv: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CUDA-core attention for odd head sizes / few queries: q [B*Nq, H*dqk], k [B*Nk, H*dqk], v [B*Nk, H*dv]."""
+    lib = _lib.load()
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    if out is None:
+        out = torch.empty((B * Nq, H * dv), dtype=torch.float16, device=q.device)
+    rc = lib.ih_attention_small_f16(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(),
+                                    _rows(v, "v"), out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, dqk, dv,
+                                    float(scale), _stream())
+    check(rc, "ih_attention_small_f16")
     return out
 
 

@@ -24,6 +24,7 @@ extern "C" {
 #define IH_EPI_NONE 0
 #define IH_EPI_GEGLU 1 /* out[:, j] = (acc[:, j] + b[j]) * gelu_erf(acc[:, F + j] + b[F + j]),  N = 2F */
 #define IH_EPI_SILU 2  /* out = silu(acc + bias) */
+#define IH_EPI_GELU 4  /* out = gelu_erf(acc + bias) */
 
 const char* ih_last_error(void);
 int ih_version(void);
@@ -68,12 +69,20 @@ int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void*
 int ih_layernorm_f16(const void* x, const void* gamma, const void* beta, void* out, int rows, int C, float eps,
                      void* stream);
 
-/* Small-M linear (M <= 8 rows): out[m, n] = act_out(W[n,:] . act_in(x[m,:]) + b[n]) + addend[m, n]; act: 0 none, 1 SiLU.
+/* Small-M linear (M <= 64 rows): out[m, n] = act_out(W[n,:] . act_in(x[m,:]) + b[n]) * out_scale + addend[m, n];
+ * act: 0 none, 1 SiLU.
  * Time / added-condition embeddings and the 17 time_emb_proj layers (diffusers), ImageProjModel / HarmonyAttention
  * linears (ip_adapter.py:41-48, train.py:243-266). */
 int ih_linear_small_f16(const void* x, long long ldx, const void* w, const void* bias, const void* addend,
                         long long ld_add, void* out, long long ldo, int M, int N, int K, int act_in, int act_out,
-                        void* stream);
+                        float out_scale, void* stream);
+
+/* Small generic attention on CUDA cores: out = softmax(q k^T / scale) v, head dims dqk / dv <= 128, Nk <= 1024,
+ * B*H*Nq a multiple of 4.  HarmonyAttention's Cross_Attention (attention_processor.py:35-56; head_dim 40, v_dim 64,
+ * scale = sqrt(40) is a divisor as in the reference), once per generate(). */
+int ih_attention_small_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                           void* out, long long ldo, int B, int H, int Nq, int Nk, int dqk, int dv, float scale,
+                           void* stream);
 
 /* Sinusoidal embedding (flip_sin_to_cos, shift 0): out[i, :] = [cos(t_i f), sin(t_i f)], f = 10000^(-j/half). t fp32.
  * step_i32 == NULL: t_i = t_f32[i]; else every row uses t_f32[*step_i32] (device-resident step counter, so the
