@@ -161,15 +161,17 @@ def cpu_unet_seconds(lat: int, repeats: int, warm: int, budget_s: float = 60.0):
     torch.set_num_threads(best_thr)
     cpu_unet_seconds.threads = best_thr
     times = []
-    t_start = time.time()
     with torch.no_grad():
-        for i in range(warm + repeats):
+        # the first forward at a new shape pays oneDNN primitive creation / weight re-ordering (tens of seconds for
+        # 2.6 G parameters): always run at least one untimed forward, outside the budget
+        for _ in range(max(1, warm)):
+            m(x, 500.0, ehs, te, tid)
+        t_start = time.time()
+        for i in range(repeats):
             t0 = time.time()
             m(x, 500.0, ehs, te, tid)
-            dt = time.time() - t0
-            if i >= warm:
-                times.append(dt)
-            if time.time() - t_start > budget_s and times:
+            times.append(time.time() - t0)
+            if time.time() - t_start > budget_s:
                 break
     times.sort()
     return times[len(times) // 2], len(times)

@@ -38,6 +38,8 @@ SIGNATURES = {
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ih_attention_small_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                        c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ih_add_bcast_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
+    "ih_mean_tokens_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ih_sinusoid_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "ih_upsample2x_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ih_concat_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p]),

@@ -337,6 +337,49 @@ __global__ void attention_small_kernel(const __half* __restrict__ q, long long l
   }
 }
 
+// out[i] = a[i] + b[i % period]  (16-byte vectors; period in elements, multiple of 8)
+__global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                 long long nvec, long long period_vec) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = a[i], y = b[i % period_vec];
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_half2(xw[e]), g = unpack_half2(yw[e]);
+      o[e] = pack_half2(f.x + g.x, f.y + g.y);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[b, :] = mean over n of x[b, n, :]   (fp32 accumulation; one thread per 8 channels)
+__global__ void mean_tokens_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= D) return;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float v[8];
+    ld8(x + ((long long)b * n + i) * D + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += v[e];
+  }
+  uint4 o;
+  const float inv = 1.f / (float)n;
+  o.x = pack_half2(acc[0] * inv, acc[1] * inv);
+  o.y = pack_half2(acc[2] * inv, acc[3] * inv);
+  o.z = pack_half2(acc[4] * inv, acc[5] * inv);
+  o.w = pack_half2(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(out + (long long)b * D + c) = o;
+}
+
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -451,5 +494,19 @@ extern "C" int ih_attention_small_f16(const void* q, long long ldq, const void* 
   IH_CUDA(launch_kernel(attention_small_kernel, dim3(blocks), dim3(warps * 32), (size_t)(warps * Nk * sizeof(float)), (cudaStream_t)stream, 
       (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo, H, Nq, Nk, dqk, dv,
       scale));
+  return 0;
+}
+
+extern "C" int ih_add_bcast_f16(const void* a, const void* b, void* out, long long n, long long period, void* stream) {
+  IH_CHECK(a && b && out && n % 8 == 0 && period % 8 == 0 && period > 0, IH_ERR_ARG, "ih_add_bcast_f16: bad arguments");
+  IH_CUDA(launch_kernel(add_bcast_kernel, dim3(grid_for(n / 8, 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        (const uint4*)a, (const uint4*)b, (uint4*)out, n / 8, period / 8));
+  return 0;
+}
+
+extern "C" int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D, void* stream) {
+  IH_CHECK(x && out && D % 8 == 0 && n > 0, IH_ERR_ARG, "ih_mean_tokens_f16: bad arguments");
+  IH_CUDA(launch_kernel(mean_tokens_kernel, dim3((D / 8 + 127) / 128, B), dim3(128), (size_t)0, (cudaStream_t)stream,
+                        (const __half*)x, (__half*)out, n, D));
   return 0;
 }

@@ -22,7 +22,7 @@ class DenoiseEngine:
         self.unet = unet
         self.device = unet.conv_in.weight.device
         self.scheduler = EulerDiscreteScheduler()
-        self.use_cuda_graph = use_cuda_graph
+        self.use_cuda_graph = use_cuda_graph and self.device.type == "cuda"
         self._graphs: Dict[Tuple, torch.cuda.CUDAGraph] = {}
         self._static: Dict[Tuple, dict] = {}
         self._tables: Dict[int, Tuple[torch.Tensor, torch.Tensor, float]] = {}

@@ -196,6 +196,32 @@ def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H
     return out
 
 
+def add_bcast(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a + b where b is broadcast over the leading elements of a (a.numel() % b.numel() == 0), contiguous fp16."""
+    lib = _lib.load()
+    _req(a, "a"); _req(b, "b")
+    if not (a.is_contiguous() and b.is_contiguous()) or a.numel() % b.numel() != 0:
+        raise IHError("add_bcast: contiguous tensors with a.numel() % b.numel() == 0 required")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.ih_add_bcast_f16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), b.numel(), _stream()),
+          "ih_add_bcast_f16")
+    return out
+
+
+def mean_tokens(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, n, D] -> [B, D] mean over tokens."""
+    lib = _lib.load()
+    _req(x, "x")
+    B, n, D = x.shape
+    if not x.is_contiguous():
+        raise IHError("mean_tokens: x must be contiguous")
+    if out is None:
+        out = torch.empty((B, D), dtype=torch.float16, device=x.device)
+    check(lib.ih_mean_tokens_f16(x.data_ptr(), out.data_ptr(), B, n, D, _stream()), "ih_mean_tokens_f16")
+    return out
+
+
 def sinusoid(t: torch.Tensor, dim: int, n: int, *, step: Optional[torch.Tensor] = None,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n, dim] fp16 sinusoidal embedding of fp32 `t` (or of t[step] for every row when `step` is given)."""

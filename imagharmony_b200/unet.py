@@ -363,7 +363,9 @@ class UNet2DConditionModel(nn.Module):
         cfg = self.config
         ehs = encoder_hidden_states
         B, L, _ = ehs.shape
-        n_text = L - cfg.num_ip_tokens
+        n_ip = next((p.num_tokens for p in self.attn_processors.values() if hasattr(p, "num_tokens")),
+                    cfg.num_ip_tokens)
+        n_text = L - n_ip
         text_only = ehs[:, :n_text].contiguous()
         self._text_only = text_only
         for name, attn in self._attn_modules():

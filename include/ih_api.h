@@ -89,6 +89,11 @@ int ih_attention_small_f16(const void* q, long long ldq, const void* k, long lon
  * timestep of custom_pipelines.py:325 can live inside a replayed CUDA graph). */
 int ih_sinusoid_f16(const void* t_f32, const void* step_i32, void* out, long long ldo, int n, int dim, void* stream);
 
+/* out[i] = a[i] + b[i % period]: residual / positional-embedding adds of the Resampler (resampler.py:128-131,143-144). */
+int ih_add_bcast_f16(const void* a, const void* b, void* out, long long n, long long period, void* stream);
+/* out[b, :] = mean_n x[b, n, :]  -- Resampler masked_mean with an all-ones mask (resampler.py:137-138,150-158). */
+int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D, void* stream);
+
 /* Nearest-neighbour 2x upsample NHWC [B,H,W,C] -> [B,2H,2W,C]. */
 int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream);
 

@@ -28,6 +28,9 @@ def _merge_heads(x: torch.Tensor) -> torch.Tensor:
 def _sdpa(q, k, v):
     """softmax(q k^T / sqrt(d)) v -- what F.scaled_dot_product_attention computes with no mask, p=0
     (attention_processor.py:312-314, 423-425, 440-442). Written out so the oracle does not depend on SDPA backends."""
+    if q.is_cuda:
+        # on a GPU the oracle doubles as the "reference GPU path" stand-in: call the very function the reference calls
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     return torch.matmul(torch.softmax(s, dim=-1), v)
 

@@ -21,8 +21,8 @@ def _f(t):
     return None if t is None else t.float()
 
 
-def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, out=None,
-           tile_n=0):
+def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, gelu=False,
+           out=None, tile_n=0):
     _count[0] += 1
     y = x.float() @ w.float().t()
     if bias is not None:
@@ -34,6 +34,8 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
         y = y + rowbias.float().repeat_interleave(rows_per_group, dim=0)
     if silu:
         y = F.silu(y)
+    if gelu:
+        y = F.gelu(y)
     if residual is not None:
         y = y + residual.float()
     y = y.to(x.dtype)
@@ -41,6 +43,25 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
         out.copy_(y)
         return out
     return y
+
+
+def attention_small(q, k, v, B, H, Nq, Nk, dqk, dv, scale, out=None):
+    _count[0] += 1
+    qf = q.float().reshape(B, Nq, H, dqk).transpose(1, 2)
+    kf = k.float().reshape(B, Nk, H, dqk).transpose(1, 2)
+    vf = v.float().reshape(B, Nk, H, dv).transpose(1, 2)
+    o = torch.softmax(qf @ kf.transpose(-1, -2) / scale, -1) @ vf
+    return o.transpose(1, 2).reshape(B * Nq, H * dv).to(q.dtype)
+
+
+def add_bcast(a, b, out=None):
+    _count[0] += 1
+    return (a.reshape(-1, b.numel()) + b.reshape(1, -1)).reshape(a.shape)
+
+
+def mean_tokens(x, out=None):
+    _count[0] += 1
+    return x.mean(dim=1)
 
 
 def pack_conv3x3_weight(w):
@@ -88,7 +109,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps).to(x.dtype)
 
 
-def linear_small(x, w, bias=None, *, act_in=False, act_out=False, addend=None, out=None):
+def linear_small(x, w, bias=None, *, act_in=False, act_out=False, addend=None, out_scale=1.0, out=None):
     _count[0] += 1
     xi = F.silu(x.float()) if act_in else x.float()
     y = xi @ w.float().t()
@@ -96,6 +117,7 @@ def linear_small(x, w, bias=None, *, act_in=False, act_out=False, addend=None, o
         y = y + bias.float()
     if act_out:
         y = F.silu(y)
+    y = y * out_scale
     if addend is not None:
         y = y + addend.float()
     y = y.to(x.dtype)
