@@ -241,6 +241,54 @@ def time_dominant_kernel(iters: int = 30):
     return 2.0 * M * N * K, sec
 
 
+def run_pns(args, eng, cfg, lat, K, W, rank, world, device, dist):
+    """PNS N candidates: shard seeds over ranks, K-step trajectories in batches, score, all_gather, argmax."""
+    from imagharmony_b200.pns import LinearProbeScorer, pns_select, shard_seeds
+    from imagharmony_b200.scheduler import EulerDiscreteScheduler
+    N = args.pns
+    seeds = [5000 + i for i in range(N)]
+    ins = EulerDiscreteScheduler().set_timesteps(K).init_noise_sigma
+    _, pos1, neg1, pooled1, npooled1, tid1 = synth_inputs(cfg, 1, lat, K, 0)
+
+    def run_candidates(batch_seeds):
+        b = len(batch_seeds)
+        lat0 = torch.cat([torch.randn((1, 4, lat, lat), generator=torch.Generator("cpu").manual_seed(s))
+                          for s in batch_seeds]) * ins
+        rep = lambda t: t.repeat(b, *([1] * (t.dim() - 1))).pin_memory()  # noqa: E731
+        return eng.run(lat0.half().pin_memory(), rep(pos1), rep(neg1), rep(pooled1), rep(npooled1), rep(tid1), K,
+                       guidance_scale=5.0, ip_scale=1.0)
+
+    scorer = LinearProbeScorer(4 * lat * lat, seed=99, device=device)
+    mine = shard_seeds(seeds, rank, world)
+    if mine:                                           # warm-up: capture the graphs for this rank's batch sizes
+        for bsz in sorted({min(args.pns_batch, len(mine)), len(mine) % args.pns_batch or args.pns_batch}):
+            eng.run(*[t.pin_memory() for t in synth_inputs(cfg, bsz, lat, K, rank)], K, stop_after=W)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = pns_select(run_candidates, seeds, scorer, dist=dist, max_batch=args.pns_batch)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([wall], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall = float(tt[0])
+    if rank == 0:
+        line = {"metric": METRIC + " -- PNS", "value": N * K / wall, "unit": "denoise-steps/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": f"PNS N={N} candidate noises, {args.res}x{args.res}, {K} steps each, "
+                                       f"{args.pns_batch} candidates per batch, score = fixed random linear probe of the "
+                                       f"final latent, all_gather of N fp32 scores + broadcast of the winner",
+                           "pns_edits_per_s": N / wall, "pns_wall_s": wall, "best_seed": res.best_seed},
+                "e2e": {"value": N * K / wall, "unit": "denoise-steps/s",
+                        "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "note": "PNS wall clock includes H2D of every candidate batch and the score gather"},
+                "gpu_launches": int(eng.last_launches_per_step * K * ((len(mine) + args.pns_batch - 1) // args.pns_batch))}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -250,6 +298,9 @@ def main():
     ap.add_argument("--images", type=int, default=1, help="images (noise candidates) per GPU; UNet batch = 2x (CFG)")
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pns", type=int, default=0,
+                    help="PNS mode: N candidate noises in total, sharded over the ranks (BASELINE config 4: N=32 on 8 GPUs)")
+    ap.add_argument("--pns-batch", type=int, default=4, help="candidates denoised together per rank (UNet batch 2x)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -274,6 +325,12 @@ def main():
     lat = args.res // 8
     unet = build_native(cfg, device)
     eng = DenoiseEngine(unet, use_cuda_graph=True)
+    if args.pns > 0:
+        run_pns(args, eng, cfg, lat, K, W, rank, world, device, dist)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     latents, pos, neg, pooled, npooled, tid = [t.pin_memory() for t in synth_inputs(cfg, n, lat, K, rank)]
 
     def barrier():

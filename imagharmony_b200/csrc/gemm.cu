@@ -16,6 +16,7 @@
 // (proj_in/out, FF GEGLU) and Conv2d.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/ih_api.h"
 #include "host_util.h"
@@ -53,9 +54,10 @@ struct GemmParams {
   int act;  // 0 none, 1 SiLU, 2 GELU(erf) (applied after bias, before residual)
 };
 
-template <int BN, int STAGES, bool GEGLU>
+template <int BN, int STAGES, bool GEGLU, bool PAIR = false>
 struct GemmSmem {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  // PAIR (cta_group::2): each CTA of the pair stages its own 128 A rows and HALF of the B tile
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
@@ -69,11 +71,15 @@ constexpr int GEMM_THREADS_P = (2 + GEMM_EPI_WARPS) * 32;  // warp 0 TMA, warp 1
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The smem stage
 // ring runs continuously across tiles, and the fp32 accumulator is double-buffered in TMEM so that the epilogue of
 // tile i (TMEM -> registers -> global, 8 warps) overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, int STAGES, bool GEGLU>
+// PAIR = true: the two CTAs of a cluster (one TPC) compute one 256 x BN tile with tcgen05.mma.cta_group::2 -- each SM
+// feeds its own 128 A rows and half of B from its shared memory, which halves the per-SM operand traffic that bounds
+// the single-CTA tile.  The leader CTA (cluster rank 0) issues every MMA; both CTAs run TMA producers whose loads
+// complete on the leader's mbarriers; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
+template <int BN, int STAGES, bool GEGLU, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __grid_constant__ TmapSet4 amaps,
                                                                       const __grid_constant__ CUtensorMap bmap,
                                                                       const GemmParams p) {
-  using S = GemmSmem<BN, STAGES, GEGLU>;
+  using S = GemmSmem<BN, STAGES, GEGLU, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
@@ -86,7 +92,13 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
   const int lane = threadIdx.x & 31;
   constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
   const int n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
-  const int num_tiles = n_tiles * p.m_tiles;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  // work items: (m_unit, n_tile); an m_unit is one 128-row tile, or a pair of them (256 rows) in PAIR mode
+  const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int num_tiles = n_tiles * m_units;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&amaps.m[0]);
@@ -97,13 +109,17 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * (PAIR ? 2 : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm<S::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<S::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's mbarriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();  // the next kernel may begin its prologue now ...
@@ -114,11 +130,11 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int n_tile = tile % n_tiles;
-        const int m_tile = tile / n_tiles;
+        const int m_tile = PAIR ? 2 * (tile / n_tiles) + (int)cta_rank : tile / n_tiles;
         const int n0 = n_tile * BN_OUT;
-        const int m0 = m_tile * BM;
+        const int m0 = m_tile * BM;   // a dead half-tile (m_tile == m_tiles) loads zero-filled rows
         int img = 0, x0 = 0, y0 = 0;
         if (p.mode == 1) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -131,20 +147,36 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          if (p.mode == 0) {
-            tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
+          if (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            if (p.mode == 0) {
+              tma_load_2d_2sm(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
+            } else {
+              const int tap = kb / p.cin_kb;
+              const int ckb = kb - tap * p.cin_kb;
+              tma_load_4d_2sm(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
+                              y0 + p.tap_oy[tap], img);
+            }
+            // B half: leader = first BN/2 rows of the tile (GEGLU: value rows), peer = second half (GEGLU: gate rows)
+            const int brow = GEGLU ? (leader ? n0 : p.gate_row_off + n0) : n0 + (int)cta_rank * (BN / 2);
+            tma_load_2d_2sm(sB, &bmap, &full_bar[stage], kb * BK, brow);
           } else {
-            const int tap = kb / p.cin_kb;
-            const int ckb = kb - tap * p.cin_kb;
-            tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
-                        y0 + p.tap_oy[tap], img);
-          }
-          if (GEGLU) {
-            tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
-            tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
-          } else {
-            tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            if (p.mode == 0) {
+              tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
+            } else {
+              const int tap = kb / p.cin_kb;
+              const int ckb = kb - tap * p.cin_kb;
+              tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
+                          y0 + p.tap_oy[tap], img);
+            }
+            if (GEGLU) {
+              tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+              tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
+            } else {
+              tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -155,12 +187,12 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -175,15 +207,18 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-            umma_f16_ss(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_f16_ss_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (PAIR) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (PAIR) umma_commit_2sm(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
     __syncwarp();
@@ -195,9 +230,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     constexpr int CHUNKS = BN_OUT / 32;   // 32-column chunks per tile
     constexpr int CPW = (CHUNKS + 1) / 2; // chunks per warp
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int n_tile = tile % n_tiles;
-      const int m_tile = tile / n_tiles;
+      const int m_tile = PAIR ? 2 * (tile / n_tiles) + (int)cta_rank : tile / n_tiles;
       const int n0 = n_tile * BN_OUT;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -206,6 +241,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       if (p.mode == 0) {
         orow = (long long)m_tile * BM + r;
         row_ok = orow < p.M;
+      } else if (m_tile >= p.m_tiles) {
+        orow = 0;
+        row_ok = false;
       } else {
         const int per_img = p.tiles_x * p.tiles_y;
         const int img = m_tile / per_img;
@@ -239,7 +277,10 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           // all of this warp's TMEM reads of the accumulator are complete: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         if (live && row_ok) {
 #pragma unroll
@@ -318,25 +359,37 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<S::TMEM_COLS>(tmem_base);
+  if (PAIR) cluster_sync_all();   // nobody may exit (or free TMEM) while the peer can still signal / read it
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2sm<S::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<S::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool GEGLU>
+template <int BN, int STAGES, bool GEGLU, bool PAIR = false>
 static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES, GEGLU>;
+  using S = GemmSmem<BN, STAGES, GEGLU, PAIR>;
   static bool configured = false;
-  auto kern = gemm_f16_kernel<BN, STAGES, GEGLU>;
+  auto kern = gemm_f16_kernel<BN, STAGES, GEGLU, PAIR>;
   if (!configured) {
     IH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
   p.m_tiles = m_tiles;
-  const long long tiles = (long long)((p.N + BN_OUT - 1) / BN_OUT) * m_tiles;
+  const long long n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
+  if (PAIR) {
+    const long long units = n_tiles * ((m_tiles + 1) / 2);
+    const long long pairs = num_sms() / 2;
+    const int grid = 2 * (int)(units < pairs ? units : pairs);
+    IH_CUDA(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, 2, amaps, bmap, p));
+    return 0;
+  }
+  const long long tiles = n_tiles * m_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   IH_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, amaps, bmap, p));
   return 0;
@@ -367,15 +420,45 @@ static int pick_bn(long long m_tiles, int N) {
   return best_bn;
 }
 
+// IH_GEMM_PAIR: 0 = never use the CTA-pair tile, 1 = cost model (default), 2 = whenever N >= 256
+static int pair_mode() {
+  static int m = [] {
+    const char* e = getenv("IH_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  return m;
+}
+static bool pair_is_faster(long long m_tiles, int n_cols, bool geglu) {
+  const int sms = num_sms();
+  const long long nt = (n_cols + 255) / 256;
+  const long long r1 = (m_tiles * nt + sms - 1) / sms;                       // single-CTA 128x256 tiles
+  const long long r2 = (((m_tiles + 1) / 2) * nt + sms / 2 - 1) / (sms / 2);  // pair 256x256 tiles
+  const double t1 = (double)r1 * (2.0 + 0.15), t2 = (double)r2 * (2.0 / 1.3 + 0.15);
+  (void)geglu;
+  return t2 < t1;
+}
+
 static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long long K, GemmParams& p, int m_tiles,
                     int geglu, int force_bn, cudaStream_t stream) {
-  int bn = geglu ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
+  // tile_n = 512 forces the CTA-pair 256x256 tile, other explicit values force the single-CTA tile of that width
+  bool pair = false;
+  if (force_bn == 512) {
+    pair = true;
+    force_bn = 256;
+  } else if (force_bn == 0 && pair_mode() != 0 && (geglu || p.N >= 256)) {
+    pair = pair_mode() == 2 || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, geglu);
+  }
+  int bn = (geglu || pair) ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
   CUtensorMap bmap;
   const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)ldw_rows};
   const uint64_t bstr[1] = {(uint64_t)K * 2};
-  const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(geglu ? 128 : bn)};
+  const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)((geglu || pair) ? 128 : bn)};
   int rc = get_tmap_f16(&bmap, w, 2, bdims, bstr, bbox);
   if (rc) return rc;
+  if (pair) {
+    if (geglu) return launch_gemm<256, 6, true, true>(amaps, bmap, p, m_tiles, stream);
+    return launch_gemm<256, 6, false, true>(amaps, bmap, p, m_tiles, stream);
+  }
   if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, p, m_tiles, stream);
   switch (bn) {
     case 256: return launch_gemm<256, 4, false>(amaps, bmap, p, m_tiles, stream);

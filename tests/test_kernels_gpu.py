@@ -52,6 +52,11 @@ def check(out, ref, what, rtol=RTOL, atol=ATOL):
     (8192, 320, 320, 128),    # N = 2.5 tiles
     (1000, 1920, 640, 0),
     (300, 72, 200, 64),       # K not a multiple of 64 (TMA zero-fill), N not a multiple of 64
+    (256, 256, 64, 512),      # CTA-pair (cta_group::2) 256x256 tile, single k-block
+    (2048, 1280, 1280, 512),  # CTA pair, persistent over several tiles
+    (8192, 640, 2560, 512),   # CTA pair, partially filled N tile (640 = 2.5 x 256)
+    (384, 3840, 1280, 512),   # CTA pair, odd number of 128-row tiles (dead half tile)
+    (1000, 1920, 640, 512),
 ])
 def test_gemm_plain(ops, M, N, K, tile_n):
     x = rnd(M, K)
@@ -81,12 +86,13 @@ def test_gemm_epilogues(ops):
     assert (obuf[:, :N] == 0).all()
 
 
+@pytest.mark.parametrize("tile_n", [256, 512])
 @pytest.mark.parametrize("M,C", [(2048, 1280), (512, 640), (100, 640)])
-def test_gemm_geglu(ops, M, C):
+def test_gemm_geglu(ops, M, C, tile_n):
     x = rnd(M, C)
     w = rnd(8 * C, C, scale=C ** -0.5)
     b = rnd(8 * C)
-    out = ops.linear(x, w, b, geglu=True)
+    out = ops.linear(x, w, b, geglu=True, tile_n=tile_n)
     h = x.float() @ w.float().t() + b.float()
     a, g = h.chunk(2, dim=-1)
     check(out, a * F.gelu(g), f"geglu {M}x{C}")
@@ -114,6 +120,19 @@ def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
     out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), b, stride=stride)
     ref = F.conv2d(x_nchw.float(), w.float(), b.float(), stride=stride, padding=1).permute(0, 2, 3, 1)
     check(out, ref, f"conv3x3 {B}x{H}x{W} {Cin}->{Cout} s{stride}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
+    (2, 32, 32, 1280, 1280, 1), (2, 64, 64, 640, 640, 1), (1, 24, 24, 128, 320, 1), (2, 64, 64, 320, 320, 2),
+])
+def test_conv3x3_cta_pair(ops, B, H, W, Cin, Cout, stride):
+    x_nchw = rnd(B, Cin, H, W)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = rnd(Cout)
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), b, stride=stride, tile_n=512)
+    ref = F.conv2d(x_nchw.float(), w.float(), b.float(), stride=stride, padding=1).permute(0, 2, 3, 1)
+    check(out, ref, f"conv3x3 pair {B}x{H}x{W} {Cin}->{Cout} s{stride}")
 
 
 def test_conv3x3_epilogue(ops):

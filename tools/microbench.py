@@ -47,12 +47,16 @@ def main():
         res.append(d)
         print(json.dumps(d), flush=True)
 
-    for (M, N, K, geglu, tn) in [(2048, 10240, 1280, True, 0), (2048, 1280, 5120, False, 0), (2048, 1280, 5120, False, 64),
-                                 (2048, 3840, 1280, False, 0), (2048, 3840, 1280, False, 256),
-                                 (2048, 1280, 1280, False, 0), (2048, 1280, 1280, False, 64),
-                                 (8192, 5120, 640, True, 0), (8192, 640, 2560, False, 0), (8192, 1920, 640, False, 0),
-                                 (8192, 640, 640, False, 0), (16384, 10240, 1280, True, 0), (16384, 1280, 5120, False, 0),
-                                 (8192, 8192, 8192, False, 256), (8192, 8192, 8192, False, 128)]:
+    for (M, N, K, geglu, tn) in [(2048, 10240, 1280, True, 256), (2048, 10240, 1280, True, 512),
+                                 (2048, 1280, 5120, False, 128), (2048, 1280, 5120, False, 256), (2048, 1280, 5120, False, 512),
+                                 (2048, 3840, 1280, False, 256), (2048, 3840, 1280, False, 512),
+                                 (2048, 1280, 1280, False, 128), (2048, 1280, 1280, False, 256), (2048, 1280, 1280, False, 512),
+                                 (8192, 5120, 640, True, 256), (8192, 5120, 640, True, 512),
+                                 (8192, 640, 2560, False, 256), (8192, 640, 2560, False, 512),
+                                 (8192, 1920, 640, False, 256), (8192, 1920, 640, False, 512),
+                                 (8192, 640, 640, False, 128), (8192, 640, 640, False, 512),
+                                 (16384, 10240, 1280, True, 512), (16384, 1280, 5120, False, 512),
+                                 (8192, 8192, 8192, False, 256), (8192, 8192, 8192, False, 512)]:
         x, w, b = r(M, K), r(N, K, scale=K ** -0.5), r(N)
         try:
             t = timeit(lambda: ops.linear(x, w, b, geglu=geglu, tile_n=tn))
@@ -66,11 +70,12 @@ def main():
         x = r(B, H, H, Cin)
         w = r(Cout, 9 * Cin, scale=(9 * Cin) ** -0.5)
         b = r(Cout)
-        try:
-            t = timeit(lambda: ops.conv3x3(x, w, b, stride=s))
-            rec(f"conv3x3 B{B} {H}^2 {Cin}->{Cout} s{s}", t, 2.0 * B * (H // s) ** 2 * Cout * 9 * Cin)
-        except Exception as ex:  # noqa
-            print("ERR conv", B, H, Cin, Cout, ex)
+        for tn in (128, 256, 512):
+            try:
+                t = timeit(lambda: ops.conv3x3(x, w, b, stride=s, tile_n=tn))
+                rec(f"conv3x3 B{B} {H}^2 {Cin}->{Cout} s{s} bn{tn}", t, 2.0 * B * (H // s) ** 2 * Cout * 9 * Cin)
+            except Exception as ex:  # noqa
+                print("ERR conv", B, H, Cin, Cout, ex)
 
     for (B, H, N, Nk, nip) in [(2, 10, 4096, 4096, 0), (2, 20, 1024, 1024, 0), (16, 20, 1024, 1024, 0), (2, 20, 1024, 81, 4),
                                (2, 10, 4096, 77, 0), (16, 10, 4096, 4096, 0)]:
