@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&p_full[t], 128);
       mbar_init(&o_full[t], 1);
     }
     for (int s = 0; s < A2_KS; ++s) {
@@ -466,98 +466,85 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
         const int valid = p.Nk - j * 128;
-        float m_blk = -INFINITY;
+        // pass 1: row max (two 32-column TMEM loads in flight per wait)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(tS + hlf * 64, va);
+          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
+          tmem_ld_wait();
+          if (valid < 128) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;  // -inf
+              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmax3(mx0, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(vb[e]), __uint_as_float(vb[e + 1]));
+          }
+        }
+        const float m_blk = fmaxf(mx0, mx1) * sl2;
         if (j == 0) {
-          // first block: explicit max pass (two 32-column TMEM loads in flight per wait)
-          float mx0 = -INFINITY, mx1 = -INFINITY;
+          m_used = m_blk;
+        } else {
+          const bool need = m_blk > m_used + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? m_blk : m_used;
+            const float alpha = ex2_approx(m_used - m_new);
+            m_used = m_new;
+            l_run *= alpha;
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t va[32], vb[32];
-            tmem_ld_32x32b_x32(tS + hlf * 64, va);
-            tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
-            tmem_ld_wait();
-            if (valid < 128) {
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld_32x32b_x32(tO + c * 32, ov);
+              tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                if (hlf * 64 + e >= valid) va[e] = 0xff800000u;  // -inf
-                if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
-              }
+              for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+              tmem_st_32x32b_x32(tO + c * 32, ov);
             }
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              mx0 = fmax3(mx0, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
-              mx1 = fmax3(mx1, __uint_as_float(vb[e]), __uint_as_float(vb[e + 1]));
-            }
+            tmem_st_wait();
           }
-          m_used = fmaxf(mx0, mx1) * sl2;
         }
-        // probabilities p = 2^(s*scale - m_used) -> fp16 P tile (A operand of the PV MMA) and row sum, in ONE pass over
-        // S.  For j > 0 the reference max is the one carried from earlier blocks ("lazy max"); the block's own max is
-        // tracked alongside and, only if it exceeds m_used by more than 2^8 (rare after the first blocks), O and l are
-        // rescaled and the pass is repeated with the raised max.
-        float rowsum = 0.f;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
-          float sum0 = 0.f, sum1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 1
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t va[32], vb[32];
-            tmem_ld_32x32b_x32(tS + hlf * 64, va);
-            tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
-            tmem_ld_wait();
-            if (valid < 128) {
+        // pass 2: p = 2^(s*scale - m) -> fp16 P tile (A operand of the PV MMA), row sum
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                if (hlf * 64 + e >= valid) va[e] = 0xff800000u;
-                if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
-              }
-            }
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(tS + hlf * 64, va);
+          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
+          tmem_ld_wait();
+          if (valid < 128) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint32_t* src = (g < 4) ? (va + g * 8) : (vb + (g - 4) * 8);
-              float pr[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pr[e] = ex2_approx(fmaf(__uint_as_float(src[e]), sl2, -m_used));
-              mx0 = fmax3(mx0, __uint_as_float(src[0]), __uint_as_float(src[1]));
-              mx1 = fmax3(mx1, __uint_as_float(src[2]), __uint_as_float(src[3]));
-              mx0 = fmax3(mx0, __uint_as_float(src[4]), __uint_as_float(src[5]));
-              mx1 = fmax3(mx1, __uint_as_float(src[6]), __uint_as_float(src[7]));
-              sum0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
-              sum1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
-              uint4 o;
-              o.x = pack_half2(pr[0], pr[1]);
-              o.y = pack_half2(pr[2], pr[3]);
-              o.z = pack_half2(pr[4], pr[5]);
-              o.w = pack_half2(pr[6], pr[7]);
-              // 16-byte chunk g of key half `hlf`, XOR-swizzled with the row (SWIZZLE_128B)
-              *reinterpret_cast<uint4*>(p_row + hlf * ATT_TILE + ((g ^ rx) << 4)) = o;
+            for (int e = 0; e < 32; ++e) {
+              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;
+              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
             }
           }
-          rowsum = sum0 + sum1;
-          m_blk = fmaxf(mx0, mx1) * sl2;
-          const bool need = (j > 0) && (attempt == 0) && (m_blk > m_used + 8.0f);
-          if (!__any_sync(0xffffffffu, need)) break;
-          // raise the reference max for the rows that need it, rescale their O row (and l), then redo the pass
-          const float m_new = need ? m_blk : m_used;
-          const float alpha = ex2_approx(m_used - m_new);
-          m_used = m_new;
-          l_run *= alpha;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(tO + c * 32, ov);
-            tmem_ld_wait();
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t* src = (g < 4) ? (va + g * 8) : (vb + (g - 4) * 8);
+            float pr[8];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-            tmem_st_32x32b_x32(tO + c * 32, ov);
+            for (int e = 0; e < 8; ++e) pr[e] = ex2_approx(fmaf(__uint_as_float(src[e]), sl2, -m_used));
+            sum0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
+            sum1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
+            uint4 o;
+            o.x = pack_half2(pr[0], pr[1]);
+            o.y = pack_half2(pr[2], pr[3]);
+            o.z = pack_half2(pr[4], pr[5]);
+            o.w = pack_half2(pr[6], pr[7]);
+            // 16-byte chunk g of key half `hlf`, XOR-swizzled with the row (SWIZZLE_128B)
+            *reinterpret_cast<uint4*>(p_row + hlf * ATT_TILE + ((g ^ rx) << 4)) = o;
           }
-          tmem_st_wait();
         }
-        l_run += rowsum;
+        l_run += sum0 + sum1;
         tc_fence_before();
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);   // one arrival per warp (barrier count = 4)
+        mbar_arrive(&p_full[t]);
       }
 
       // epilogue: O / l -> global

@@ -274,7 +274,10 @@ class UNetRef(nn.Module):
         cfg = self.config
         dt = sample.dtype
         b = sample.shape[0]
-        t = torch.as_tensor(timestep, dtype=torch.float32, device=sample.device).reshape(-1).expand(b)
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=sample.device, dtype=torch.float32).reshape(-1).expand(b)
+        else:
+            t = torch.full((b,), float(timestep), dtype=torch.float32, device=sample.device)
         emb = self.time_embedding(sinusoidal_embedding(t, cfg.block_out_channels[0]).to(dt))
         tid = sinusoidal_embedding(time_ids.reshape(-1), cfg.addition_time_embed_dim).reshape(b, -1)
         aug = self.add_embedding(torch.cat([text_embeds, tid.to(text_embeds.dtype)], dim=-1).to(dt))
