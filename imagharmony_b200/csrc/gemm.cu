@@ -123,27 +123,11 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();  // the next kernel may begin its prologue now ...
-  // ... and nobody may touch activations before our predecessor has finished.  Weights (the B operand) never depend
-  // on a previous kernel and stream from HBM (the 5.2 GB model does not fit in L2), so the producer first warms L2 with
-  // the weight tiles of its first k-blocks and only then waits.
-  constexpr int PF = 8;  // L2 prefetch distance in k-blocks
-  auto b_rows = [&](int n0, int which) -> int {   // row coordinate(s) of this CTA's B box(es) for an output tile
-    if (PAIR) return GEGLU ? (leader ? n0 : p.gate_row_off + n0) : n0 + (int)cta_rank * (BN / 2);
-    return which == 0 ? n0 : p.gate_row_off + n0;
-  };
-  if (!(warp == 0 && lane == 0)) pdl_wait();
+  pdl_wait();               // ... and we may not touch global memory before our predecessor has finished
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      if (worker < num_tiles) {
-        const int n0f = (worker % n_tiles) * BN_OUT;
-        for (int kb = 0; kb < PF && kb < p.num_kb; ++kb) {
-          tma_prefetch_l2_2d(&bmap, kb * BK, b_rows(n0f, 0));
-          if (GEGLU && !PAIR) tma_prefetch_l2_2d(&bmap, kb * BK, b_rows(n0f, 1));
-        }
-      }
-      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -192,20 +176,6 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               tma_load_2d(sB + (BN / 2) * BK * 2, &bmap, &full_bar[stage], kb * BK, p.gate_row_off + n0);
             } else {
               tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
-            }
-          }
-          {  // keep L2 PF k-blocks ahead of the TMA loads (runs into the next tile of this CTA)
-            int pk = kb + PF, pn0 = n0;
-            bool ok = true;
-            if (pk >= p.num_kb) {
-              pk -= p.num_kb;
-              const int nt = tile + num_workers;
-              ok = (nt < num_tiles) && (pk < p.num_kb);
-              pn0 = (nt % n_tiles) * BN_OUT;
-            }
-            if (ok) {
-              tma_prefetch_l2_2d(&bmap, pk * BK, b_rows(pn0, 0));
-              if (GEGLU && !PAIR) tma_prefetch_l2_2d(&bmap, pk * BK, b_rows(pn0, 1));
             }
           }
           if (++stage == STAGES) {

@@ -119,6 +119,13 @@ bool pdl_enabled() {
   return on;
 }
 
+bool first_launch_of(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, bool> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  return seen.emplace(kern, true).second;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

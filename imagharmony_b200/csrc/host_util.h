@@ -36,6 +36,16 @@ void count_launch(int n = 1);
 // descriptor prefetch, CTA scheduling) with the previous kernel's tail.  IH_PDL=0 in the environment disables it.
 bool pdl_enabled();
 
+// Every kernel of the library asks for the maximum shared-memory carve-out, so that consecutive kernels never force
+// the SMs to re-partition L1/shared memory (a drain + reconfiguration between e.g. LayerNorm and a 193 KiB GEMM).
+// Returns true the first time a kernel pointer is seen.
+bool first_launch_of(const void* kern);
+template <typename K>
+inline void prefer_max_smem_carveout(K kern) {
+  if (first_launch_of(reinterpret_cast<const void*>(kern)))
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args&&... args) {
@@ -49,6 +59,7 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  prefer_max_smem_carveout(kern);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (e == cudaSuccess) count_launch();
   return e;
@@ -71,6 +82,7 @@ inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  prefer_max_smem_carveout(kern);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (e == cudaSuccess) count_launch();
   return e;
