@@ -428,13 +428,16 @@ static int pair_mode() {
   }();
   return m;
 }
-static bool pair_is_faster(long long m_tiles, int n_cols, bool geglu) {
+// Measured on B200 (tools/overhead_probe.py, tools/microbench.py): a cluster launch + two cluster barriers cost ~5 us
+// more than a plain launch (10.7 vs 5.7 us for a one-tile GEMM) while the pair main loop is only ~5 % faster than
+// the single-CTA 128x256 tile, so the pair tile pays off only for long-running GEMMs.
+static bool pair_is_faster(long long m_tiles, int n_cols, int num_kb) {
   const int sms = num_sms();
   const long long nt = (n_cols + 255) / 256;
   const long long r1 = (m_tiles * nt + sms - 1) / sms;                       // single-CTA 128x256 tiles
   const long long r2 = (((m_tiles + 1) / 2) * nt + sms / 2 - 1) / (sms / 2);  // pair 256x256 tiles
-  const double t1 = (double)r1 * (2.0 + 0.15), t2 = (double)r2 * (2.0 / 1.3 + 0.15);
-  (void)geglu;
+  const double kb_us = 0.30;
+  const double t1 = (double)r1 * num_kb * kb_us + 5.7, t2 = (double)r2 * num_kb * kb_us / 1.05 + 10.7;
   return t2 < t1;
 }
 
@@ -446,7 +449,7 @@ static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long lon
     pair = true;
     force_bn = 256;
   } else if (force_bn == 0 && pair_mode() != 0 && (geglu || p.N >= 256)) {
-    pair = pair_mode() == 2 || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, geglu);
+    pair = pair_mode() == 2 || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, p.num_kb);
   }
   int bn = (geglu || pair) ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
   CUtensorMap bmap;

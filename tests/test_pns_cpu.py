@@ -1,27 +1,16 @@
 """PNS shard / score all_gather / argmax on two CPU processes over gloo (the N>1 host logic of bench.py --pns)."""
 import os
 import socket
+import subprocess
+import sys
 
 import torch
-import torch.multiprocessing as mp
 
 from imagharmony_b200.pns import LinearProbeScorer, pns_select, shard_seeds
 
-
-def _fake_runner(seeds):
-    # stands in for DenoiseEngine.run: latents are a deterministic function of the seed only (placement invariant)
-    return torch.cat([torch.randn((1, 4, 8, 8), generator=torch.Generator("cpu").manual_seed(int(s))) for s in seeds]).half()
-
-
-def _worker(rank, world, port, seeds, q):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    res = pns_select(_fake_runner, seeds, LinearProbeScorer(4 * 8 * 8, seed=5), dist=dist, max_batch=2)
-    q.put((rank, res.scores.clone(), res.best_index, res.best_seed, res.best_latents.clone()))
-    dist.barrier()
-    dist.destroy_process_group()
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from pns_worker import fake_runner  # noqa: E402
 
 
 def _free_port():
@@ -40,20 +29,17 @@ def test_shard_seeds_covers_everything_once():
     assert shard_seeds([1, 2, 3], 5, 8) == []          # a rank with zero candidates
 
 
-def test_pns_two_ranks_gloo_matches_single_process():
+def test_pns_two_ranks_gloo_matches_single_process(tmp_path):
     seeds = [11, 12, 13, 14, 15]                        # uneven shards: 3 + 2
-    single = pns_select(_fake_runner, seeds, LinearProbeScorer(4 * 8 * 8, seed=5), dist=None, max_batch=2)
-    ctx = mp.get_context("fork")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, seeds, q)) for r in range(2)]
+    single = pns_select(fake_runner, seeds, LinearProbeScorer(4 * 8 * 8, seed=5), dist=None, max_batch=2)
+    port = str(_free_port())
+    outs = [str(tmp_path / f"r{r}.pt") for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "pns_worker.py"), str(r), "2", port, outs[r],
+                               ",".join(map(str, seeds))]) for r in range(2)]
     for p in procs:
-        p.start()
-    got = [q.get(timeout=120) for _ in range(2)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    for rank, scores, bi, bs, lat in got:
-        assert torch.allclose(scores, single.scores, atol=1e-5)
-        assert bi == single.best_index and bs == single.best_seed
-        assert torch.equal(lat, single.best_latents)      # every rank ends up with the winner's latents
+        assert p.wait(timeout=180) == 0
+    for o in outs:
+        got = torch.load(o)
+        assert torch.allclose(got["scores"], single.scores, atol=1e-5)
+        assert got["best_index"] == single.best_index and got["best_seed"] == single.best_seed
+        assert torch.equal(got["best_latents"], single.best_latents)   # every rank ends up with the winner's latents

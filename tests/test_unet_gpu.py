@@ -173,3 +173,119 @@ def test_denoise_loop_tiny_matches_oracle(use_graph):
                      control_guidance_end=0.75)
         assert torch.equal(o, o2)
         assert eng.last_launches_per_step > 50
+
+
+def test_adapter_modules_match_reference_goldens_on_gpu():
+    """HarmonyAttention / ImageProjModel / Resampler on the kernels vs outputs of the reference's own classes
+    (train.py:188-266, ip_adapter.py:28-48, resampler.py:81-147), parameters and inputs rounded to fp16."""
+    from imagharmony_b200 import adapter as N
+    from oracle import adapter_ref as A
+    gold = torch.load(GOLDEN, map_location="cpu")
+
+    def h(sd):
+        return {k: v.half() for k, v in sd.items()}
+
+    g = gold["harmony"]
+    ha = N.HarmonyAttention(fusion_method="cross_attention", **g["kwargs"])
+    ha.load_state_dict(g["state"])
+    ha = ha.half().cuda()
+    ref = A.HarmonyAttentionRef(**g["kwargs"])
+    ref.load_state_dict({k: v.half().float() for k, v in g["state"].items()})
+    text, img = g["text"].half(), g["image"].half()
+    want = ref(text.float(), img.float())
+    got = ha(text.cuda(), img.cuda())
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float().cpu(), want, rtol=5e-3, atol=5e-3), (got.float().cpu() - want).abs().max()
+    assert (got.float().cpu() - g["out"]).abs().max() < 3e-2
+    fused = ha(text.cuda(), img.cuda(), add_to=img.cuda())
+    assert torch.allclose(fused.float().cpu(), img.float() + want, rtol=5e-3, atol=5e-3)
+
+    g = gold["imageproj"]
+    ip = N.ImageProjModel(128, 64, 4)
+    ip.load_state_dict(g["state"])
+    ip = ip.half().cuda()
+    rip = A.ImageProjRef(128, 64, 4)
+    rip.load_state_dict({k: v.half().float() for k, v in g["state"].items()})
+    x = g["image"].half()
+    assert torch.allclose(ip(x.cuda()).float().cpu(), rip(x.float()), rtol=5e-3, atol=5e-3)
+
+    g = gold["resampler"]
+    r = N.Resampler(**g["kwargs"])
+    r.load_state_dict(g["state"])
+    r = r.half().cuda()
+    rr = A.ResamplerRef(**g["kwargs"])
+    rr.load_state_dict({k: v.half().float() for k, v in g["state"].items()})
+    x = g["x"].half()
+    got = r(x.cuda())
+    torch.cuda.synchronize()
+    want = rr(x.float())
+    assert got.shape == (2, 12, 160)
+    assert torch.allclose(got.float().cpu(), want, rtol=1e-2, atol=1e-2), (got.float().cpu() - want).abs().max()
+
+
+def test_ip_adapter_xl_generate_on_gpu_matches_oracle_latents():
+    """The reference call surface on the GPU: IPAdapterXL.generate(...) (HA -> ImageProj -> 81-token embeds ->
+    CUDA-graph denoise loop) against the oracle pipeline assembled from oracle/ pieces with the same weights."""
+    from imagharmony_b200.config import HARMONY_TINY, TINY
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    from ip_adapter import IPAdapterXL
+    from ip_adapter.custom_pipelines import StableDiffusionXLCustomPipeline
+    from oracle import adapter_ref as A
+    from oracle.scheduler_ref import denoise_loop, euler_tables
+    from oracle.unet_ref import UNetRef
+    from train import HarmonyAttention
+
+    cfg, h = TINY, HARMONY_TINY
+    with torch.device("meta"):
+        shapes = shapes_of(UNetRef(cfg))
+    sd = random_state_dict(shapes, 11)
+    from imagharmony_b200.unet import UNet2DConditionModel
+    pipe = StableDiffusionXLCustomPipeline(UNet2DConditionModel.from_state_dict(cfg, sd, device="cuda"))
+    kw = dict(image_hidden_size=h.image_hidden_size, text_context_dim=h.text_context_dim, inter_dim=h.inter_dim,
+              cross_heads=h.cross_heads, reshape_blocks=h.reshape_blocks, cross_value_dim=h.cross_value_dim, scale=1.0)
+    ha = HarmonyAttention(fusion_method="cross_attention", **kw)
+    ip_model = IPAdapterXL(pipe, None, None, "cuda", num_tokens=4, inference=True, number_class_crossattention=ha)
+    ck = {"image_proj": random_state_dict(shapes_of(ip_model.image_proj_model), 3),
+          "composed_adapter": random_state_dict(shapes_of(ha), 4),
+          "ip_adapter": random_state_dict(shapes_of(torch.nn.ModuleList(pipe.unet.attn_processors.values())), 5)}
+    ip_model.image_proj_model.load_state_dict({k: v.cuda() for k, v in ck["image_proj"].items()})
+    ip_model.number_class_crossattention.load_state_dict({k: v.cuda() for k, v in ck["composed_adapter"].items()})
+    torch.nn.ModuleList(pipe.unet.attn_processors.values()).load_state_dict({k: v.cuda() for k, v in ck["ip_adapter"].items()})
+    pipe.unet.finalize()
+    img = torch.randn(1, h.image_hidden_size, generator=torch.Generator("cpu").manual_seed(5)).half()
+    T, res = 3, 256
+    out = ip_model.generate(pil_image=None, clip_image_embeds=img, prompt="lions", negative_prompt="blurry", scale=0.8,
+                            guidance_scale=5.0, num_samples=1, num_inference_steps=T, seed=[42], extra_text="eight sheep",
+                            output_type="latent", height=res, width=res)
+    torch.cuda.synchronize()
+    # ---- the same thing from oracle parts (fp32, CPU) ----
+    ref_unet = UNetRef(cfg)
+    ref_unet.load_state_dict({k: v.float() for k, v in sd.items()})
+    pr = A.install_processors(ref_unet, cfg)
+    torch.nn.ModuleList(pr.values()).load_state_dict({k: v.float() for k, v in ck["ip_adapter"].items()})
+    ref_unet.eval()
+    rha = A.HarmonyAttentionRef(**kw)
+    rha.load_state_dict({k: v.float() for k, v in ck["composed_adapter"].items()})
+    rip = A.ImageProjRef(cfg.cross_attention_dim, h.image_hidden_size, 4)
+    rip.load_state_dict({k: v.float() for k, v in ck["image_proj"].items()})
+    enc = pipe.prompt_encoder
+    pe, pp = enc(["lions"])
+    ne, npool = enc(["blurry"])
+    xe, _ = enc(["eight sheep"])
+    with torch.no_grad():
+        emb = img.float() + rha(xe.float(), img.float())
+        cond, uncond = rip(emb), rip(torch.zeros_like(emb))
+    pos = torch.cat([pe.float(), cond], dim=1)
+    neg = torch.cat([ne.float(), uncond], dim=1)
+    _, _, ins = euler_tables(T)
+    lat = (torch.randn((1, 4, res // 8, res // 8), generator=torch.Generator("cpu").manual_seed(42)) * ins).half()
+    tid = torch.tensor([[res, res, 0, 0, res, res]], dtype=torch.float32)
+    procs = [p for p in ref_unet.attn_processors.values() if hasattr(p, "to_k_ip")]
+    for p in procs:
+        p.scale = 0.8
+    want = denoise_loop(lambda s, t, e, a, b: ref_unet(s.float(), t, e, a, b).half(), lat, pos, neg, pp.float(),
+                        npool.float(), tid, T, guidance_scale=5.0)
+    err = (out.float().cpu() - want.float()).abs().max().item()
+    mx = want.float().abs().max().item()
+    print(f"[IPAdapterXL.generate tiny] max|err| {err:.3e} max|ref| {mx:.3e}")
+    assert err <= 2e-2 * mx, (err, mx)
