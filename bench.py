@@ -144,22 +144,8 @@ def cpu_unet_seconds(lat: int, repeats: int, warm: int, budget_s: float = 60.0):
     ehs = torch.randn(2, 81, cfg.cross_attention_dim, generator=g)
     te = torch.randn(2, cfg.pooled_embed_dim, generator=g)
     tid = torch.tensor([[lat * 8.0, lat * 8.0, 0, 0, lat * 8.0, lat * 8.0]] * 2)
-    # "all the host threads it can use": oversubscribing small ops is slower, so pick the best of a few counts
-    cores = os.cpu_count() or 1
-    best_thr, best_t = cores, None
-    xs = torch.randn(2, 4, 16, 16, generator=g)
-    tids = torch.tensor([[128.0, 128.0, 0, 0, 128.0, 128.0]] * 2)
-    with torch.no_grad():
-        for thr in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
-            torch.set_num_threads(thr)
-            m(xs, 500.0, ehs, te, tids)
-            t0 = time.time()
-            m(xs, 500.0, ehs, te, tids)
-            dt = time.time() - t0
-            if best_t is None or dt < best_t:
-                best_thr, best_t = thr, dt
-    torch.set_num_threads(best_thr)
-    cpu_unet_seconds.threads = best_thr
+    # all host threads torch's intra-op pool uses by default (= physical cores visible to the process)
+    cpu_unet_seconds.threads = torch.get_num_threads()
     times = []
     with torch.no_grad():
         # the first forward at a new shape pays oneDNN primitive creation / weight re-ordering (tens of seconds for
@@ -191,8 +177,8 @@ def run_reference_arm(args):
     est_step_s = sec * (13.524 / flop_sample)
     value = args.images / est_step_s
     cores = getattr(cpu_unet_seconds, "threads", os.cpu_count() or 1)
-    sample = (f"CPU oracle (port of the reference PyTorch path, fp32, {cores} of {os.cpu_count()} host threads -- best "
-              f"of a thread-count probe): median of {n} UNet forwards on a "
+    sample = (f"CPU oracle (port of the reference PyTorch path, fp32, {cores} intra-op threads of {os.cpu_count()} logical "
+              f"CPUs): median of {n} UNet forwards on a "
               f"CFG pair at {lat_sample * 8}^2, scaled to 1024^2 by the algorithmic FLOP ratio")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": est_step_s * 1e3, "higher_is_better": True,

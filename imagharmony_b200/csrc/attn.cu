@@ -296,6 +296,200 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_f16_kernel(const __grid_c
 
 
 // ================================================================================================================
+// Cross-attention with a short key axis (Nk <= 96: 77 text tokens, optionally + the image-prompt tokens).
+// One CTA = 128 query rows of one (batch, head); ~73 KiB of shared memory and 128 TMEM columns so that THREE CTAs
+// share an SM and a whole SDXL layer (320 / 640 CTAs) runs in one / two waves -- the op is a latency chain
+// (TMA -> S MMA -> softmax -> PV MMA -> store), not a throughput problem.  S = Q K^T is a single 128x96 MMA tile; the
+// row thread runs the text softmax over columns [0, n_text) and, for the 10 IMAGHarmony layers, an independent softmax
+// over the image columns [n_text, Nk), writes [P_t/l_t | scale*P_ip/l_ip] as the fp16 A operand and ONE PV MMA yields
+// softmax(q k_t^T) v_t + scale * softmax(q k_ip^T) v_ip  (attention_processor.py:423-450).  O overlays S in TMEM.
+// ================================================================================================================
+constexpr int AX_THREADS = 192;
+constexpr int AX_KV_TILE = 96 * 64 * 2;                                   // 12 KiB: 96 keys x 64 fp16
+constexpr int AX_SMEM_TILES = ATT_TILE + 2 * AX_KV_TILE + 2 * ATT_TILE;   // Q | K | V | P (2 key halves)
+constexpr int AX_SMEM_BYTES = AX_SMEM_TILES + 128;
+
+__global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE;
+  uint8_t* sV = sK + AX_KV_TILE;
+  uint8_t* sP = sV + AX_KV_TILE;   // 1024-aligned: 16384 + 2 * 12288 = 40960
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AX_SMEM_TILES);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(qk_full, ATT_TILE + AX_KV_TILE);
+      tma_load_3d(sQ, &tmQ, qk_full, head * 64, q0, b);
+      tma_load_3d(sK, &tmK, qk_full, head * 64, 0, b);
+      mbar_arrive_expect_tx(v_full, AX_KV_TILE);
+      tma_load_3d(sV, &tmV, v_full, head * 64, 0, b);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
+      mbar_wait(qk_full, 0);
+      tc_fence_after();
+      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+      umma_commit(s_full);
+      mbar_wait(p_full, 0);
+      mbar_wait(v_full, 0);
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(sV);
+#pragma unroll
+      for (int kk = 0; kk < 6; ++kk) {
+        const uint64_t p_desc = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * ATT_TILE) + 2 * (kk & 3);
+        const uint64_t v_desc = umma_desc_sw128(v_addr + kk * 2048);
+        umma_f16_ss(tmem_base, p_desc, v_desc, idesc_o, kk != 0);   // O overlays the (already consumed) S columns
+      }
+      umma_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* p_row = sP + r * 128;
+    const int rx = r & 7;
+    const float sl2 = p.scale_log2;
+    const int valid = p.Nk;              // <= 96
+    const int n_text = valid - p.n_ip;
+
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    // pass 1: maxima of the two segments
+    float mx_t = -INFINITY, mx_i = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tS + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col = c * 32 + e;
+        const float s = __uint_as_float(v[e]);
+        if (col < n_text) mx_t = fmaxf(mx_t, s);
+        else if (col < valid) mx_i = fmaxf(mx_i, s);
+      }
+    }
+    const float m_t = mx_t * sl2, m_i = mx_i * sl2;
+    // pass 2: denominators
+    float l_t = 0.f, l_i = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tS + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col = c * 32 + e;
+        const float s = __uint_as_float(v[e]);
+        if (col < n_text) l_t += ex2_approx(fmaf(s, sl2, -m_t));
+        else if (col < valid) l_i += ex2_approx(fmaf(s, sl2, -m_i));
+      }
+    }
+    const float inv_t = 1.f / l_t;
+    const float inv_i = (p.n_ip > 0) ? p.ip_scale / l_i : 0.f;
+    // pass 3: normalised probabilities -> fp16 P tile (keys 96..127 of the second half are never read by the MMA)
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tS + c * 32, v);
+      tmem_ld_wait();
+      float pr[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col = c * 32 + e;
+        const float s = __uint_as_float(v[e]);
+        float pv = 0.f;
+        if (col < n_text) pv = ex2_approx(fmaf(s, sl2, -m_t)) * inv_t;
+        else if (col < valid) pv = ex2_approx(fmaf(s, sl2, -m_i)) * inv_i;
+        pr[e] = pv;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = c * 4 + g;
+        uint4 o;
+        o.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
+        o.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
+        o.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
+        o.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(p_row + (chunk >> 3) * ATT_TILE + (((chunk & 7) ^ rx) << 4)) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_full);
+
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qrow = q0 + r;
+    __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(tS + c * 32, ov);
+      tmem_ld_wait();
+      if (qrow < p.Nq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]), __uint_as_float(ov[g * 8 + 1]));
+          o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]), __uint_as_float(ov[g * 8 + 3]));
+          o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]), __uint_as_float(ov[g * 8 + 5]));
+          o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]), __uint_as_float(ov[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// ================================================================================================================
 // v2: ping-pong flash attention.  One CTA = 256 query rows (two 128-row tiles A/B) of one (batch, head); 10 warps:
 // warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax of tile A, warps 6-9 softmax of tile B.  While one tile's
 // softmax runs on the CUDA cores / MUFU, the tensor core executes the other tile's S = Q K^T and O += P V.
@@ -629,6 +823,28 @@ extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, lon
                                  cudaSharedmemCarveoutMaxShared));
     IH_CUDA(cudaFuncSetAttribute(attn2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
     configured = true;
+  }
+  if (Nk <= 96) {
+    static bool cfg_x = false;
+    if (!cfg_x) {
+      IH_CUDA(cudaFuncSetAttribute(attnx_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM_BYTES));
+      cfg_x = true;
+    }
+    CUtensorMap tkx, tvx;
+    const uint32_t boxkv[3] = {64u, 96u, 1u};
+    {
+      const uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)Nk, (uint64_t)B};
+      const uint64_t strk[2] = {(uint64_t)ldk * 2, (uint64_t)Nk * ldk * 2};
+      const uint64_t strv[2] = {(uint64_t)ldv * 2, (uint64_t)Nk * ldv * 2};
+      int rc = get_tmap_f16(&tkx, k, 3, dims, strk, boxkv);
+      if (rc) return rc;
+      rc = get_tmap_f16(&tvx, v, 3, dims, strv, boxkv);
+      if (rc) return rc;
+    }
+    dim3 gridx((Nq + 127) / 128, H, B);
+    IH_CUDA(launch_kernel(attnx_f16_kernel, gridx, dim3(AX_THREADS), (size_t)AX_SMEM_BYTES, (cudaStream_t)stream, tq, tkx,
+                          tvx, p));
+    return 0;
   }
   if (n_ip == 0) {
     dim3 grid2((Nq + 255) / 256, H, B);
