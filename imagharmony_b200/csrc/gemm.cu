@@ -52,6 +52,7 @@ struct GemmParams {
   __half* out;
   long long ldo;
   int act;  // 0 none, 1 SiLU, 2 GELU(erf) (applied after bias, before residual)
+  unsigned long long* trace;  // optional: %globaltimer stamps of CTA 0 (ih_gemm_set_trace), nullptr in production
 };
 
 template <int BN, int STAGES, bool GEGLU, bool PAIR = false>
@@ -60,8 +61,9 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = 2 * BM * 64 * 2;  // two 128-row x 64-column fp16 epilogue staging slabs (TMA store)
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TOTAL = TILE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
@@ -78,18 +80,30 @@ constexpr int GEMM_THREADS_P = (2 + GEMM_EPI_WARPS) * 32;  // warp 0 TMA, warp 1
 template <int BN, int STAGES, bool GEGLU, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __grid_constant__ TmapSet4 amaps,
                                                                       const __grid_constant__ CUtensorMap bmap,
+                                                                      const __grid_constant__ CUtensorMap omap,
+                                                                      const __grid_constant__ CUtensorMap rmap,
                                                                       const GemmParams p) {
   using S = GemmSmem<BN, STAGES, GEGLU, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+  uint8_t* stg = smem + S::TILE_BYTES;            // [2] epilogue staging slabs, 16 KiB each (1024-aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [2] residual slab landed (one per epilogue half-group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto stamp = [&](int slot) {
+    if (p.trace && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.trace[slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
   constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
   const int n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -107,7 +121,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    tma_prefetch_desc(&omap);
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&res_bar[a], 1);
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * (PAIR ? 2 : 1));
     }
@@ -122,8 +138,10 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
   if (PAIR) cluster_sync_all();   // the peer's mbarriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
   pdl_launch_dependents();  // the next kernel may begin its prologue now ...
   pdl_wait();               // ... and we may not touch global memory before our predecessor has finished
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -200,6 +218,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (it == 0 && kb == 0) stamp(3);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
@@ -223,12 +242,20 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (8 warps) ------------------------
+    // ------------------------------ epilogue (8 warps = two half-groups of 128 rows) ------------------------
+    // Each half-group drains every other 64-column slab of the accumulator: TMEM -> registers (one row per thread)
+    // -> bias / activation / GEGLU / residual -> fp16 row segment (128 B) into a 128B-swizzled staging slab ->
+    // one TMA store per slab (fully coalesced, clipped at the M / N / image edges by the tensor map).  The residual
+    // slab is TMA-loaded into the same staging buffer first and updated in place.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp drains
+    const int half = (warp - 2) >> 2;     // half-group: owns staging slab `half`
     const int r = q * 32 + lane;
-    constexpr int CHUNKS = BN_OUT / 32;   // 32-column chunks per tile
-    constexpr int CPW = (CHUNKS + 1) / 2; // chunks per warp
+    const bool elected = (q == 0 && lane == 0);
+    uint8_t* my_stg = stg + half * (BM * 128);
+    uint8_t* my_row = my_stg + r * 128;
+    const int rx = r & 7;
+    constexpr int SLABS = (BN_OUT + 63) / 64;
+    uint32_t res_phase = 0;
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int n_tile = tile % n_tiles;
@@ -236,61 +263,84 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       const int n0 = n_tile * BN_OUT;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      bool row_ok;
       long long orow;
+      int img = 0, x0 = 0, y0 = 0;
+      bool tile_live = m_tile < p.m_tiles;
       if (p.mode == 0) {
         orow = (long long)m_tile * BM + r;
-        row_ok = orow < p.M;
-      } else if (m_tile >= p.m_tiles) {
-        orow = 0;
-        row_ok = false;
       } else {
         const int per_img = p.tiles_x * p.tiles_y;
-        const int img = m_tile / per_img;
+        img = m_tile / per_img;
         const int t = m_tile - img * per_img;
-        const int y0 = (t / p.tiles_x) * p.bh, x0 = (t % p.tiles_x) * p.bw;
+        y0 = (t / p.tiles_x) * p.bh;
+        x0 = (t % p.tiles_x) * p.bw;
         const int hh = r / p.bw, ww = r - hh * p.bw;
-        const int y = y0 + hh, x = x0 + ww;
-        row_ok = (y < p.Ho) && (x < p.Wo);
+        int y = y0 + hh, x = x0 + ww;
+        if (y >= p.Ho) y = p.Ho - 1;   // clamped rows are clipped by the TMA store; keep the row-bias index in range
+        if (x >= p.Wo) x = p.Wo - 1;
         orow = ((long long)img * p.Ho + y) * p.Wo + x;
       }
       const __half* rb = nullptr;
-      if (p.rowbias && row_ok) rb = p.rowbias + (orow / p.rows_per_group) * p.ld_rowbias;
+      if (p.rowbias && tile_live) {
+        long long grp = orow / p.rows_per_group;
+        const long long max_grp = ((long long)p.M - 1) / p.rows_per_group;
+        if (grp > max_grp) grp = max_grp;
+        rb = p.rowbias + grp * p.ld_rowbias;
+      }
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (threadIdx.x == 64) stamp(4 + (it < 3 ? it : 3));
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
+      int last_slab = -1;
+      for (int sl = half; sl < SLABS; sl += 2)
+        if (n0 + sl * 64 < p.N) last_slab = sl;
+      bool arrived = false;
 #pragma unroll 1
-      for (int ci = 0; ci < CPW; ++ci) {
-        const int c = half * CPW + ci;
-        const int col0 = n0 + c * 32;
-        const bool live = (c < CHUNKS) && (col0 < p.N);   // warp-uniform
-        uint32_t v[32];
-        uint32_t g[32];
-        if (live) {
-          tmem_ld_32x32b_x32(taddr + c * 32, v);
-          if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, g);
-          tmem_ld_wait();
-        }
-        if (ci == CPW - 1) {
-          // all of this warp's TMEM reads of the accumulator are complete: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
-            else mbar_arrive(&tmem_empty_bar[acc]);
+      for (int sl = half; sl < SLABS; sl += 2) {
+        const int col0 = n0 + sl * 64;
+        const bool live = tile_live && (col0 < p.N);   // uniform over the half-group
+        if (live && p.residual) {
+          if (elected) {
+            mbar_arrive_expect_tx(&res_bar[half], BM * 128);
+            if (p.mode == 0) tma_load_2d(my_stg, &rmap, &res_bar[half], col0, m_tile * BM);
+            else tma_load_4d(my_stg, &rmap, &res_bar[half], col0, x0, y0, img);
           }
         }
-        if (live && row_ok) {
+        if (live && p.residual) {
+          mbar_wait(&res_bar[half], res_phase);
+          res_phase ^= 1;
+        }
+#pragma unroll 1
+        for (int h32 = 0; h32 < 2; ++h32) {
+          uint32_t v[32];
+          uint32_t g[32];
+          if (live) {
+            tmem_ld_32x32b_x32(taddr + sl * 64 + h32 * 32, v);
+            if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64 + h32 * 32, g);
+            tmem_ld_wait();
+          }
+          if (sl == last_slab && h32 == 1) {
+            // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
+            arrived = true;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+          }
+          if (live) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = col0 + j * 8;
-            if (col < p.N) {
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int j = h32 * 4 + j4;
+              const int col = col0 + j * 8;
               float x[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
-              if (p.bias) {
+              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j4 * 8 + e]);
+              const bool col_ok = col < p.N;   // columns past N are clipped by the store; skip their bias loads
+              if (p.bias && col_ok) {
                 const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + col);
                 const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -303,8 +353,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               if (GEGLU) {
                 float gt[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j * 8 + e]);
-                if (p.bias) {
+                for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j4 * 8 + e]);
+                if (p.bias && col_ok) {
                   const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col);
                   const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -317,7 +367,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
               }
-              if (rb) {
+              if (rb && col_ok) {
                 const uint4 b4 = *reinterpret_cast<const uint4*>(rb + col);
                 const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -334,8 +384,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
               }
+              uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ rx) << 4));
               if (p.residual) {
-                const uint4 b4 = *reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+                const uint4 b4 = *slot;
                 const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -349,16 +400,37 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               o.y = pack_half2(x[2], x[3]);
               o.z = pack_half2(x[4], x[5]);
               o.w = pack_half2(x[6], x[7]);
-              *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = o;
+              *slot = o;
             }
           }
         }
+        if (live) {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + half, 128);
+          if (elected) {
+            if (p.mode == 0) tma_store_2d(&omap, my_stg, col0, m_tile * BM);
+            else tma_store_4d(&omap, my_stg, col0, x0, y0, img);
+            tma_store_commit();
+            tma_store_wait_read0();   // the staging slab may be overwritten once the store has read it
+          }
+          named_bar_sync(1 + half, 128);
+        }
+      }
+      if (!arrived) {   // this half-group had no live slab in the tile (narrow N, dead half tile): still release
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
       }
     }
+    if (elected) tma_store_wait_all();   // global writes complete before the CTA exits
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(8);
   if (PAIR) cluster_sync_all();   // nobody may exit (or free TMEM) while the peer can still signal / read it
   if (warp == 1) {
     if (PAIR) tmem_dealloc_2sm<S::TMEM_COLS>(tmem_base);
@@ -370,8 +442,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool GEGLU, bool PAIR = false>
-static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, GemmParams& p, int m_tiles,
-                       cudaStream_t stream) {
+static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap,
+                       const CUtensorMap& rmap, GemmParams& p, int m_tiles, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, GEGLU, PAIR>;
   static bool configured = false;
   auto kern = gemm_f16_kernel<BN, STAGES, GEGLU, PAIR>;
@@ -386,12 +458,12 @@ static int launch_gemm(const TmapSet4& amaps, const CUtensorMap& bmap, GemmParam
     const long long units = n_tiles * ((m_tiles + 1) / 2);
     const long long pairs = num_sms() / 2;
     const int grid = 2 * (int)(units < pairs ? units : pairs);
-    IH_CUDA(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, 2, amaps, bmap, p));
+    IH_CUDA(launch_kernel_cluster(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, 2, amaps, bmap, omap, rmap, p));
     return 0;
   }
   const long long tiles = n_tiles * m_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  IH_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, amaps, bmap, p));
+  IH_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS_P), (size_t)(S::TOTAL), stream, amaps, bmap, omap, rmap, p));
   return 0;
 }
 
@@ -441,8 +513,8 @@ static bool pair_is_faster(long long m_tiles, int n_cols, int num_kb) {
   return t2 < t1;
 }
 
-static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long long K, GemmParams& p, int m_tiles,
-                    int geglu, int force_bn, cudaStream_t stream) {
+static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtensorMap& rmap, const void* w, int ldw_rows,
+                    long long K, GemmParams& p, int m_tiles, int geglu, int force_bn, cudaStream_t stream) {
   // tile_n = 512 forces the CTA-pair 256x256 tile, other explicit values force the single-CTA tile of that width
   bool pair = false;
   if (force_bn == 512) {
@@ -459,21 +531,27 @@ static int dispatch(const TmapSet4& amaps, const void* w, int ldw_rows, long lon
   int rc = get_tmap_f16(&bmap, w, 2, bdims, bstr, bbox);
   if (rc) return rc;
   if (pair) {
-    if (geglu) return launch_gemm<256, 6, true, true>(amaps, bmap, p, m_tiles, stream);
-    return launch_gemm<256, 6, false, true>(amaps, bmap, p, m_tiles, stream);
+    if (geglu) return launch_gemm<256, 6, true, true>(amaps, bmap, omap, rmap, p, m_tiles, stream);
+    return launch_gemm<256, 6, false, true>(amaps, bmap, omap, rmap, p, m_tiles, stream);
   }
-  if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, p, m_tiles, stream);
+  if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, omap, rmap, p, m_tiles, stream);
   switch (bn) {
-    case 256: return launch_gemm<256, 4, false>(amaps, bmap, p, m_tiles, stream);
-    case 128: return launch_gemm<128, 6, false>(amaps, bmap, p, m_tiles, stream);
-    case 64: return launch_gemm<64, 8, false>(amaps, bmap, p, m_tiles, stream);
+    case 256: return launch_gemm<256, 4, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
+    case 128: return launch_gemm<128, 6, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
+    case 64: return launch_gemm<64, 8, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
     default: return set_error(IH_ERR_ARG, "unsupported BN %d", bn);
   }
 }
 
+static unsigned long long* g_trace = nullptr;
 }  // namespace ih
 
 using namespace ih;
+
+// debugging aid: device buffer of >= 16 uint64 that CTA 0 of subsequent GEMM launches fills with %globaltimer stamps
+// (0 kernel entry, 1 setup done, 2 predecessor finished, 3 first operands landed, 4..7 accumulator ready for tiles
+// 0..3+, 8 CTA done); pass NULL to disable.
+extern "C" void ih_gemm_set_trace(void* device_buffer) { ih::g_trace = (unsigned long long*)device_buffer; }
 
 extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                            int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
@@ -511,8 +589,23 @@ extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const vo
   p.out = (__half*)out;
   p.ldo = ldo;
   p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : 0);
+  p.trace = g_trace;
   const int m_tiles = (M + BM - 1) / BM;
-  return dispatch(amaps, w, N, K, p, m_tiles, geglu, tile_n, (cudaStream_t)stream);
+  CUtensorMap omap, rmap;
+  {
+    const uint64_t odims[2] = {(uint64_t)p.N, (uint64_t)M};
+    const uint32_t obox[2] = {64u, (uint32_t)BM};
+    const uint64_t ostr[1] = {(uint64_t)ldo * 2};
+    rc = get_tmap_f16(&omap, out, 2, odims, ostr, obox);
+    if (rc) return rc;
+    rmap = omap;
+    if (residual) {
+      const uint64_t rstr[1] = {(uint64_t)ldr * 2};
+      rc = get_tmap_f16(&rmap, residual, 2, odims, rstr, obox);
+      if (rc) return rc;
+    }
+  }
+  return dispatch(amaps, omap, rmap, w, N, K, p, m_tiles, geglu, tile_n, (cudaStream_t)stream);
 }
 
 extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias,
@@ -556,6 +649,7 @@ extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, con
   p.ldr = Cout;
   p.out = (__half*)out;
   p.ldo = Cout;
+  p.trace = g_trace;
 
   TmapSet4 amaps;
   const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
@@ -592,5 +686,18 @@ extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, con
   const int m_tiles = B * p.tiles_x * p.tiles_y;
   // weight is [Cout, 9*Cin] tap-major; when Cin is not a multiple of 64 each tap's K range is padded by TMA zero fill
   IH_CHECK(Cin % BK == 0, IH_ERR_SHAPE, "ih_conv2d_f16: Cin must be a multiple of 64 (got %d)", Cin);
-  return dispatch(amaps, w, Cout, (long long)9 * Cin, p, m_tiles, 0, tile_n, (cudaStream_t)stream);
+  CUtensorMap omap, rmap;
+  {
+    const uint64_t odims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t ostr[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+    const uint32_t obox[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+    int rc = get_tmap_f16(&omap, out, 4, odims, ostr, obox);
+    if (rc) return rc;
+    rmap = omap;
+    if (residual) {
+      rc = get_tmap_f16(&rmap, residual, 4, odims, ostr, obox);
+      if (rc) return rc;
+    }
+  }
+  return dispatch(amaps, omap, rmap, w, Cout, (long long)9 * Cin, p, m_tiles, 0, tile_n, (cudaStream_t)stream);
 }

@@ -39,6 +39,10 @@ int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, c
                 int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                 long long ldo, int M, int N, int K, int epilogue, int tile_n, void* stream);
 
+/* Debug aid: CTA 0 of later GEMM / conv launches writes %globaltimer stamps into this device buffer (>= 16 uint64);
+ * NULL disables.  Not used on the product path. */
+void ih_gemm_set_trace(void* device_buffer);
+
 /* 3x3 convolution, padding 1, stride 1|2, NHWC activations, weight [Cout, 9*Cin] (tap-major: (ky*3+kx)*Cin + c).
  * out = conv(x) + bias[Cout] + rowbias[b*ld_rowbias + c] + residual.  Replaces diffusers ResnetBlock2D / Downsample2D /
  * Upsample2D nn.Conv2d (custom_pipelines.py:338-345 -> unet forward). */
