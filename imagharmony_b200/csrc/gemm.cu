@@ -425,7 +425,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         }
       }
     }
-    if (elected) tma_store_wait_all();   // global writes complete before the CTA exits
+    // shared memory must stay valid until the last bulk store has read it; global visibility is given by kernel
+    // completion (the next kernel's griddepcontrol.wait / stream order)
+    if (elected) tma_store_wait_read0();
   }
 
   tc_fence_before();

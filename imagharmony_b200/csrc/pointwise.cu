@@ -380,6 +380,54 @@ __global__ void mean_tokens_kernel(const __half* __restrict__ x, __half* __restr
   *reinterpret_cast<uint4*>(out + (long long)b * D + c) = o;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The 4-channel ends of the UNet on the tensor-core GEMM:
+//   conv_in : im2col of the NCHW latent -> A [B*H*W, 64] (k = ci*9 + ky*3 + kx, zero padded from 36 to 64 columns),
+//             then ih_gemm_f16 with the OIHW weight flattened to [320, 36->64]
+//   conv_out: ih_conv2d_f16 with Cout padded 4 -> 16, then this gather NHWC[.., 16] -> NCHW[B, 4, H, W]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void im2col3x3_nchw_kernel(const __half* __restrict__ x, __half* __restrict__ out, int B, int Cin, int H,
+                                      int W, int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long npix = (long long)B * H * W;
+  const int kv = Kpad >> 3;  // 16-byte vectors per row
+  const long long total = npix * kv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % kv);
+    const long long pix = i / kv;
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = v * 8 + e;
+      __half hv = __float2half_rn(0.f);
+      if (k < Cin * 9) {
+        const int ci = k / 9, t = k - ci * 9;
+        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) hv = x[(((long long)b * Cin + ci) * H + yy) * W + xx];
+      }
+      vals[e] = hv;
+    }
+    *reinterpret_cast<uint4*>(out + pix * Kpad + v * 8) = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, long long ldc, __half* __restrict__ out, int B,
+                                    long long HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % HW;
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / (HW * C));
+    out[i] = x[((long long)b * HW + p) * ldc + c];
+  }
+}
+
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -508,5 +556,22 @@ extern "C" int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D,
   IH_CHECK(x && out && D % 8 == 0 && n > 0, IH_ERR_ARG, "ih_mean_tokens_f16: bad arguments");
   IH_CUDA(launch_kernel(mean_tokens_kernel, dim3((D / 8 + 127) / 128, B), dim3(128), (size_t)0, (cudaStream_t)stream,
                         (const __half*)x, (__half*)out, n, D));
+  return 0;
+}
+
+extern "C" int ih_im2col3x3_nchw_f16(const void* x_nchw, void* out, int B, int Cin, int H, int W, int Kpad,
+                                     void* stream) {
+  IH_CHECK(x_nchw && out && Kpad % 8 == 0 && Kpad >= Cin * 9, IH_ERR_ARG, "ih_im2col3x3_nchw_f16: bad arguments");
+  const long long total = (long long)B * H * W * (Kpad / 8);
+  IH_CUDA(launch_kernel(im2col3x3_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        (const __half*)x_nchw, (__half*)out, B, Cin, H, W, Kpad));
+  return 0;
+}
+
+extern "C" int ih_nhwc_to_nchw_f16(const void* x, long long ldc, void* out, int B, long long HW, int C, void* stream) {
+  IH_CHECK(x && out && C >= 1, IH_ERR_ARG, "ih_nhwc_to_nchw_f16: bad arguments");
+  const long long total = (long long)B * C * HW;
+  IH_CUDA(launch_kernel(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        (const __half*)x, ldc, (__half*)out, B, HW, C));
   return 0;
 }

@@ -279,6 +279,29 @@ def conv_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Optional
     return out
 
 
+def im2col3x3_nchw(x_nchw: torch.Tensor, kpad: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, Cin, H, W] -> A [B*H*W, kpad] with k = ci*9 + ky*3 + kx (zero padded): conv_in as a tensor-core GEMM."""
+    lib = _lib.load()
+    _req(x_nchw, "x")
+    B, Cin, H, W = x_nchw.shape
+    if out is None:
+        out = torch.empty((B * H * W, kpad), dtype=torch.float16, device=x_nchw.device)
+    check(lib.ih_im2col3x3_nchw_f16(x_nchw.data_ptr(), out.data_ptr(), B, Cin, H, W, kpad, _stream()),
+          "ih_im2col3x3_nchw_f16")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, C: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x NHWC [B, H, W, ldc] -> NCHW [B, C, H, W] taking channels [0, C)."""
+    lib = _lib.load()
+    _req(x, "x")
+    B, H, W, ldc = x.shape
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float16, device=x.device)
+    check(lib.ih_nhwc_to_nchw_f16(x.data_ptr(), ldc, out.data_ptr(), B, H * W, C, _stream()), "ih_nhwc_to_nchw_f16")
+    return out
+
+
 def euler_cfg_step(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor,
                    step: torch.Tensor, guidance: float) -> None:
     lib = _lib.load()

@@ -350,6 +350,17 @@ class UNet2DConditionModel(nn.Module):
                 (m.fused_kv_weight() if m.is_cross else m.fused_qkv_weight())
         self._w_temb = torch.cat(ws, 0).contiguous()
         self._b_temb = torch.cat(bs, 0).contiguous()
+        # the 4-channel ends run on the tensor-core GEMM: conv_in weight flattened [320, 36] -> [320, 64] (zero pad);
+        # conv_out weight tap-major with Cout padded 4 -> 16
+        w_in = self.conv_in.weight.detach()
+        co, ci = w_in.shape[0], w_in.shape[1]
+        self._w_in = torch.zeros((co, 64), dtype=w_in.dtype, device=w_in.device)
+        self._w_in[:, : ci * 9] = w_in.reshape(co, ci * 9)
+        w_out = ops.pack_conv3x3_weight(self.conv_out.weight.detach())            # [4, 9*320]
+        self._w_out = torch.zeros((16, w_out.shape[1]), dtype=w_out.dtype, device=w_out.device)
+        self._w_out[: w_out.shape[0]] = w_out
+        self._b_out = torch.zeros((16,), dtype=w_out.dtype, device=w_out.device)
+        self._b_out[: w_out.shape[0]] = self.conv_out.bias.detach()
         self._aug = None
         for p in self.attn_processors.values():
             if hasattr(p, "invalidate"):
@@ -401,7 +412,8 @@ class UNet2DConditionModel(nn.Module):
                 raise IHError("forward() needs text_embeds/time_ids (or a prior prepare_conditioning())")
             self.prepare_conditioning(encoder_hidden_states, text_embeds, time_ids)
         temb_all = self.time_embeddings(timesteps, step, B)
-        x = ops.conv_in(sample, self.conv_in.weight, self.conv_in.bias)
+        Bs, _, Hs, Ws = sample.shape
+        x = ops.linear(ops.im2col3x3_nchw(sample, 64), self._w_in, self.conv_in.bias).reshape(Bs, Hs, Ws, -1)
         skips = [x]
         ehs = encoder_hidden_states
         for blk in self.down_blocks:
@@ -411,4 +423,5 @@ class UNet2DConditionModel(nn.Module):
             x = blk(x, temb_all, ehs, skips)
         x = ops.groupnorm(x, self.conv_norm_out.weight, self.conv_norm_out.bias, groups=self.config.norm_num_groups,
                           eps=1e-5, silu=True)
-        return ops.conv_out(x, self.conv_out.weight, self.conv_out.bias)
+        y16 = ops.conv3x3(x, self._w_out, self._b_out)
+        return ops.nhwc_to_nchw(y16, self.config.out_channels)

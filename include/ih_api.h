@@ -111,6 +111,12 @@ int ih_conv_in_f16(const void* x_nchw, const void* w, const void* bias, void* ou
 int ih_conv_out_f16(const void* x, const void* w, const void* bias, void* out_nchw, int B, int H, int W, int Cin,
                     int Cout, void* stream);
 
+/* conv_in on the tensor-core GEMM: im2col of the NCHW latent into A [B*H*W, Kpad] (k = ci*9 + ky*3 + kx, zero padded),
+ * to be multiplied with the OIHW weight flattened (and zero padded) to [Cout, Kpad] by ih_gemm_f16. */
+int ih_im2col3x3_nchw_f16(const void* x_nchw, void* out, int B, int Cin, int H, int W, int Kpad, void* stream);
+/* conv_out on ih_conv2d_f16 with Cout padded to 16: gather NHWC [B, HW, ldc] channels [0, C) into NCHW [B, C, HW]. */
+int ih_nhwc_to_nchw_f16(const void* x, long long ldc, void* out, int B, long long HW, int C, void* stream);
+
 /* One scheduler transition (custom_pipelines.py:332-334,348-357):
  *   eps = u + g (c - u)  (fp16 tensor arithmetic, rounded like the reference's);
  *   x <- fp16( x + ((x - (x - sigma_i eps)) / sigma_i) (sigma_{i+1} - sigma_i) )   (fp32 inside, Euler, [3P] diffusers);

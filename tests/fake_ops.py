@@ -179,3 +179,16 @@ def scale_model_input(latents, model_in, sigmas, step):
     s = float(sigmas[int(step.item())])
     mi = (latents.float() / (s * s + 1) ** 0.5).to(model_in.dtype)
     model_in.copy_(torch.cat([mi, mi]))
+
+
+def im2col3x3_nchw(x_nchw, kpad=64, out=None):
+    _count[0] += 1
+    B, C, H, W = x_nchw.shape
+    cols = F.unfold(x_nchw.float(), kernel_size=3, padding=1)            # [B, C*9, H*W], k = c*9 + ky*3 + kx
+    a = cols.transpose(1, 2).reshape(B * H * W, C * 9)
+    return F.pad(a, (0, kpad - C * 9)).to(x_nchw.dtype)
+
+
+def nhwc_to_nchw(x, C, out=None):
+    _count[0] += 1
+    return x[..., :C].permute(0, 3, 1, 2).contiguous()
