@@ -723,7 +723,11 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
             const uint32_t* src = (g < 4) ? (va + g * 8) : (vb + (g - 4) * 8);
             float pr[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) pr[e] = ex2_approx(fmaf(__uint_as_float(src[e]), sl2, -m_used));
+            for (int e = 0; e < 8; ++e) {
+              const float xarg = fmaf(__uint_as_float(src[e]), sl2, -m_used);
+              // 3 of every 8 exponentials on the FMA pipe, 5 on the MUFU pipe (balances the two pipes)
+              pr[e] = (e == 2 || e == 5 || e == 7) ? ex2_poly(xarg) : ex2_approx(xarg);
+            }
             sum0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
             sum1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
             uint4 o;

@@ -253,6 +253,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel. error 7.5e-5,
+// well below the fp16 rounding of the probabilities).  The attention softmax is MUFU-bound at head_dim 64 (measured:
+// 16 ex2/clk/SM vs 128 FMA/clk/SM, tools/ubench/pipes.cu), so a share of the exponentials is computed here, in
+// parallel with the MUFU pipe.  Valid for x <= 0 up to small positive x (the softmax argument).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;   // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float n = t - 12582912.f;
+  const float f = x - n;
+  float p = fmaf(0.05517164f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
