@@ -479,9 +479,11 @@ static int pick_bn(long long m_tiles, int N) {
   const int sms = num_sms();
   double best = 1e30;
   int best_bn = 256;
-  const int cands[2] = {256, 128};
-  const double tile_cost[2] = {2.0, 1.5};
-  for (int i = 0; i < 2; ++i) {
+  // per-tile main-loop cost relative to the 128x256 tile (narrower tiles move more operand bytes per FLOP):
+  // measured 8192^3: 256 -> 1.0, 128 -> 0.75 (not 0.5); 192 interpolated
+  const int cands[3] = {256, 192, 128};
+  const double tile_cost[3] = {2.0, 1.65, 1.5};
+  for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
     const long long rounds = (tiles + sms - 1) / sms;
@@ -539,6 +541,7 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
   if (geglu) return launch_gemm<256, 4, true>(amaps, bmap, omap, rmap, p, m_tiles, stream);
   switch (bn) {
     case 256: return launch_gemm<256, 4, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
+    case 192: return launch_gemm<192, 4, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
     case 128: return launch_gemm<128, 6, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
     case 64: return launch_gemm<64, 8, false>(amaps, bmap, omap, rmap, p, m_tiles, stream);
     default: return set_error(IH_ERR_ARG, "unsupported BN %d", bn);

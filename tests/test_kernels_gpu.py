@@ -57,6 +57,8 @@ def check(out, ref, what, rtol=RTOL, atol=ATOL):
     (8192, 640, 2560, 512),   # CTA pair, partially filled N tile (640 = 2.5 x 256)
     (384, 3840, 1280, 512),   # CTA pair, odd number of 128-row tiles (dead half tile)
     (1000, 1920, 640, 512),
+    (2048, 1280, 1280, 192),  # 128x192 tiles: 7 N tiles, the last one clipped at N
+    (300, 200, 320, 192),
 ])
 def test_gemm_plain(ops, M, N, K, tile_n):
     x = rnd(M, K)
@@ -124,6 +126,21 @@ def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
     (2, 32, 32, 1280, 1280, 1), (2, 64, 64, 640, 640, 1), (1, 24, 24, 128, 320, 1), (2, 64, 64, 320, 320, 2),
+])
+@pytest.mark.parametrize("tile_n", [512, 192])
+def test_conv3x3_tile_variants(ops, B, H, W, Cin, Cout, stride, tile_n):
+    x_nchw = rnd(B, Cin, H, W)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = rnd(Cout)
+    res = rnd(B, H // stride, W // stride, Cout, seed=21)
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), b, stride=stride, residual=res, tile_n=tile_n)
+    ref = F.conv2d(x_nchw.float(), w.float(), b.float(), stride=stride, padding=1).permute(0, 2, 3, 1) + res.float()
+    check(out, ref, f"conv3x3 bn{tile_n} {B}x{H}x{W} {Cin}->{Cout} s{stride}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
+    (2, 32, 32, 1280, 1280, 1),
 ])
 def test_conv3x3_cta_pair(ops, B, H, W, Cin, Cout, stride):
     x_nchw = rnd(B, Cin, H, W)

@@ -48,9 +48,9 @@ def main():
         print(json.dumps(d), flush=True)
 
     for (M, N, K, geglu, tn) in [(2048, 10240, 1280, True, 256), (2048, 10240, 1280, True, 512),
-                                 (2048, 1280, 5120, False, 128), (2048, 1280, 5120, False, 256), (2048, 1280, 5120, False, 512),
+                                 (2048, 1280, 5120, False, 192), (2048, 1280, 5120, False, 256), (2048, 1280, 5120, False, 0),
                                  (2048, 3840, 1280, False, 256), (2048, 3840, 1280, False, 512),
-                                 (2048, 1280, 1280, False, 128), (2048, 1280, 1280, False, 256), (2048, 1280, 1280, False, 512),
+                                 (2048, 1280, 1280, False, 192), (2048, 1280, 1280, False, 256), (2048, 1280, 1280, False, 0),
                                  (8192, 5120, 640, True, 256), (8192, 5120, 640, True, 512),
                                  (8192, 640, 2560, False, 256), (8192, 640, 2560, False, 512),
                                  (8192, 1920, 640, False, 256), (8192, 1920, 640, False, 512),
@@ -70,7 +70,7 @@ def main():
         x = r(B, H, H, Cin)
         w = r(Cout, 9 * Cin, scale=(9 * Cin) ** -0.5)
         b = r(Cout)
-        for tn in (128, 256, 512):
+        for tn in (192, 256, 0):
             try:
                 t = timeit(lambda: ops.conv3x3(x, w, b, stride=s, tile_n=tn))
                 rec(f"conv3x3 B{B} {H}^2 {Cin}->{Cout} s{s} bn{tn}", t, 2.0 * B * (H // s) ** 2 * Cout * 9 * Cin)
