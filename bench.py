@@ -31,6 +31,9 @@ import torch  # noqa: E402
 METRIC = "denoise-steps/s @1024^2 SDXL (UNet + CFG + Euler step, IMAGHarmony IP cross-attention)"
 # algorithmic FLOPs of one UNet forward per CFG pair (SURVEY.md section 8d / BASELINE.md section 3)
 TFLOP_PER_PAIR = {64: 3.179, 96: 7.284, 128: 13.524}
+# dram__bytes_read.sum + dram__bytes_write.sum of one FF GEGLU-in launch from the ncu --set full capture
+# gpurun_out/prof_geglu256_r1.ncu-rep (summary committed in profiles/r1_ncu_full_summaries.txt): 31.543 MB + 0.120 MB
+DOMINANT_KERNEL_DRAM_BYTES = 31.543e6 + 0.120e6
 
 
 def peaks():
@@ -386,7 +389,11 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_kernel<256,4,GEGLU> 2048x10240x1280 (FF GEGLU-in)",
                          "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops_burst"], "traffic": None, "peak_source": pk["source"]},
+                         "frac": achieved / pk["tflops_burst"], "traffic": DOMINANT_KERNEL_DRAM_BYTES,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, cold caches "
+                                         "(profiles/r1_ncu_full_summaries.txt); algorithmic bytes 2(MK+NK+MN/2) = "
+                                         "52.4 MB, the 21 MB output stays in L2",
+                         "peak_source": pk["source"]},
         }
         if not args.no_cpu_baseline and world == 1:
             try:
