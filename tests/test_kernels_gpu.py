@@ -218,6 +218,18 @@ def test_attention_decoupled_ip(ops, Nq, scale):
     check(out, ref_t + scale * ref_i, f"decoupled ip attn Nq{Nq} s{scale}")
 
 
+def test_attention_decoupled_ip_long_text(ops):
+    """96 < Nk <= 128 with image tokens takes the 128-key single-block kernel (attn_f16_kernel)."""
+    B, H, Nq, Nt, Ni = 2, 4, 300, 100, 16
+    C = H * 64
+    q, k, v = rnd(B * Nq, C), rnd(B * (Nt + Ni), C, seed=1), rnd(B * (Nt + Ni), C, seed=2)
+    out = ops.attention(q, k, v, B, H, Nq, Nt + Ni, n_ip=Ni, ip_scale=0.5)
+    k3, v3 = k.view(B, Nt + Ni, C), v.view(B, Nt + Ni, C)
+    ref_t = sdpa_ref(q, k3[:, :Nt].reshape(-1, C), v3[:, :Nt].reshape(-1, C), B, H, Nq, Nt)
+    ref_i = sdpa_ref(q, k3[:, Nt:].reshape(-1, C), v3[:, Nt:].reshape(-1, C), B, H, Nq, Ni)
+    check(out, ref_t + 0.5 * ref_i, "decoupled ip attn Nk=116")
+
+
 # ------------------------------------------------------------------------------------------------------------
 # norms
 # ------------------------------------------------------------------------------------------------------------

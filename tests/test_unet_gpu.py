@@ -289,3 +289,45 @@ def test_ip_adapter_xl_generate_on_gpu_matches_oracle_latents():
     mx = want.float().abs().max().item()
     print(f"[IPAdapterXL.generate tiny] max|err| {err:.3e} max|ref| {mx:.3e}")
     assert err <= 2e-2 * mx, (err, mx)
+
+
+def test_unet_forward_sdxl_base_512_matches_oracle():
+    """The full SDXL-base architecture (2.57 B parameters, 70 transformer blocks, 10 IP layers) at 512x512, UNet batch 2
+    (BASELINE config 1 shape) against the CPU fp32 oracle with identical fp16-representable random weights."""
+    from imagharmony_b200.config import SDXL_BASE as cfg
+    from imagharmony_b200.unet import UNet2DConditionModel
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    from oracle import adapter_ref as A
+    from oracle.unet_ref import UNetRef
+    with torch.device("meta"):
+        shapes = shapes_of(UNetRef(cfg))
+    sd = random_state_dict(shapes, 0, device="cuda")           # drawn on the GPU (2.6 G numbers), shared with the oracle
+    native = UNet2DConditionModel.from_state_dict(cfg, sd, device="cuda")
+    procs = torch.nn.ModuleList(native.attn_processors.values())
+    ip_sd = random_state_dict(shapes_of(procs), 1, device="cuda")
+    procs.load_state_dict(ip_sd)
+    native.finalize()
+    with torch.device("meta"):
+        ref = UNetRef(cfg)
+    ref = ref.to_empty(device="cpu")
+    ref.load_state_dict({k: v.float().cpu() for k, v in sd.items()})
+    with torch.device("meta"):
+        pr = A.install_processors(ref, cfg)
+    for p in pr.values():
+        p.to_empty(device="cpu")
+    torch.nn.ModuleList(pr.values()).load_state_dict({k: v.float().cpu() for k, v in ip_sd.items()})
+    ref.eval()
+    del sd
+    x = _inputs(cfg, 1, 64, seed=13)
+    with torch.no_grad():
+        r = ref(x["sample"].float(), 601.0, x["ehs"].float(), x["text_embeds"].float(), x["time_ids"])
+        o = native(x["sample"].cuda(), torch.full((2,), 601.0, device="cuda"), x["ehs"].cuda(), x["text_embeds"].cuda(),
+                   x["time_ids"].cuda())
+    torch.cuda.synchronize()
+    err = (o.float().cpu() - r).abs().max().item()
+    mx = r.abs().max().item()
+    rel_rms = ((o.float().cpu() - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
+    print(f"[unet SDXL-base 512^2] max|err| {err:.3e}  max|ref| {mx:.3e}  rel-RMS {rel_rms:.3e}")
+    assert torch.isfinite(o).all()
+    # ~100 fp16-rounded layers deep: bar = 1 % of the output range and 0.5 % relative RMS against the fp32 oracle
+    assert err <= 1e-2 * mx and rel_rms <= 5e-3, (err, mx, rel_rms)
