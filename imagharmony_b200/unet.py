@@ -46,6 +46,12 @@ class Attention(nn.Module):
         self.processor = None
         self._w_qkv = None
         self._w_kv = None
+        self._ln = None      # (gamma-scaled weight, ln_s, ln_c) of the projection that consumes a folded LayerNorm
+
+    def fold_ln(self, norm: nn.LayerNorm) -> None:
+        """Fold the block's LayerNorm into the first projection of this attention (q|k|v for attn1, q for attn2)."""
+        w = self.to_q.weight.detach() if self.is_cross else self.fused_qkv_weight()
+        self._ln = ops.fold_layernorm(w, None, norm.weight.detach(), norm.bias.detach())
 
     def fused_qkv_weight(self) -> torch.Tensor:
         if self._w_qkv is None:
@@ -61,10 +67,12 @@ class Attention(nn.Module):
     def drop_fused(self):
         self._w_qkv = None
         self._w_kv = None
+        self._ln = None
 
-    def forward(self, hidden_states, encoder_hidden_states=None, residual=None):
+    def forward(self, hidden_states, encoder_hidden_states=None, **fused):
+        """`fused` carries the native-processor extensions (residual=, ln_stats=, ln_eps=, stats_out=)."""
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states, attention_mask=None,
-                              residual=residual)
+                              **fused)
 
 
 class ResnetBlock2D(nn.Module):
@@ -125,18 +133,46 @@ class BasicTransformerBlock(nn.Module):
         self.attn2 = Attention(dim, heads, cross_dim)
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim)
+        self._ln_ff = None
 
-    def forward(self, h: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
-        """h [B, N, C] tokens."""
+    def finalize(self):
+        self.attn1.fold_ln(self.norm1)
+        self.attn2.fold_ln(self.norm2)
+        self._ln_ff = ops.fold_layernorm(self.ff.net[0].proj.weight.detach(), self.ff.net[0].proj.bias.detach(),
+                                         self.norm3.weight.detach(), self.norm3.bias.detach())
+
+    def _attend(self, attn, norm, h, ehs, h_stats, want_stats):
+        """h + attn(norm(h)) with the LayerNorm folded into the attention's first GEMM when row statistics of `h`
+        are available (written by the GEMM that produced `h`).  Returns (new h, its row statistics or None)."""
         B, N, C = h.shape
-        n = ops.layernorm(h, self.norm1.weight, self.norm1.bias, 1e-5)
-        h = self.attn1(n, None, residual=h)
-        n = ops.layernorm(h, self.norm2.weight, self.norm2.bias, 1e-5)
-        h = self.attn2(n, ehs, residual=h)
-        n = ops.layernorm(h, self.norm3.weight, self.norm3.bias, 1e-5)
-        g = ops.linear(n.reshape(B * N, C), self.ff.net[0].proj.weight, self.ff.net[0].proj.bias, geglu=True)
-        h2 = ops.linear(g, self.ff.net[2].weight, self.ff.net[2].bias, residual=h.reshape(B * N, C))
-        return h2.reshape(B, N, C)
+        proc = attn.processor
+        if not getattr(proc, "supports_fused", False):
+            # foreign processor: plain diffusers protocol (normalised input, no fused residual)
+            n = ops.layernorm(h, norm.weight, norm.bias, norm.eps)
+            out = proc(attn, n, encoder_hidden_states=ehs, attention_mask=None)
+            return ops.add_bcast(h, out.contiguous()), None
+        st = torch.empty((B * N, C // 64, 2), dtype=torch.float32, device=h.device) if want_stats else None
+        if h_stats is not None and attn._ln is not None:
+            return attn(h, ehs, residual=h, ln_stats=h_stats, ln_eps=norm.eps, stats_out=st), st
+        n = ops.layernorm(h, norm.weight, norm.bias, norm.eps)
+        return attn(n, ehs, residual=h, stats_out=st), st
+
+    def forward(self, h: torch.Tensor, ehs: torch.Tensor, h_stats: Optional[torch.Tensor] = None, want_stats=True):
+        """h [B, N, C] tokens; h_stats: per-row (sum, sumsq) slabs of h written by the producing GEMM (or None)."""
+        B, N, C = h.shape
+        fold = C % 64 == 0
+        h, st = self._attend(self.attn1, self.norm1, h, None, h_stats if fold else None, fold)
+        h, st = self._attend(self.attn2, self.norm2, h, ehs, st, fold)
+        h2d = h.reshape(B * N, C)
+        if st is not None and self._ln_ff is not None:
+            w_g, ln_s, ln_c = self._ln_ff
+            g = ops.linear(h2d, w_g, geglu=True, ln=(st, ln_s, ln_c, self.norm3.eps))
+        else:
+            n = ops.layernorm(h, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+            g = ops.linear(n.reshape(B * N, C), self.ff.net[0].proj.weight, self.ff.net[0].proj.bias, geglu=True)
+        st_out = torch.empty((B * N, C // 64, 2), dtype=torch.float32, device=h.device) if (fold and want_stats) else None
+        h2 = ops.linear(g, self.ff.net[2].weight, self.ff.net[2].bias, residual=h2d, stats_out=st_out)
+        return h2.reshape(B, N, C), st_out
 
 
 class Transformer2DModel(nn.Module):
@@ -151,9 +187,12 @@ class Transformer2DModel(nn.Module):
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
         h = ops.groupnorm(x, self.norm.weight, self.norm.bias, groups=self.groups, eps=1e-6, silu=False)
-        h = ops.linear(h.reshape(B * H * W, C), self.proj_in.weight, self.proj_in.bias).reshape(B, H * W, C)
-        for blk in self.transformer_blocks:
-            h = blk(h, ehs)
+        st = torch.empty((B * H * W, C // 64, 2), dtype=torch.float32, device=x.device) if C % 64 == 0 else None
+        h = ops.linear(h.reshape(B * H * W, C), self.proj_in.weight, self.proj_in.bias, stats_out=st)
+        h = h.reshape(B, H * W, C)
+        nblk = len(self.transformer_blocks)
+        for i, blk in enumerate(self.transformer_blocks):
+            h, st = blk(h, ehs, st, want_stats=i + 1 < nblk)
         out = ops.linear(h.reshape(B * H * W, C), self.proj_out.weight, self.proj_out.bias,
                          residual=x.reshape(B * H * W, C))
         return out.reshape(B, H, W, C)
@@ -340,6 +379,8 @@ class UNet2DConditionModel(nn.Module):
         for m in self.modules():
             if isinstance(m, (ResnetBlock2D, Resample)):
                 m.finalize()
+            if isinstance(m, BasicTransformerBlock):
+                m._ln_ff = None
             if isinstance(m, ResnetBlock2D):
                 m.temb_offset = offs
                 offs += m.cout
@@ -348,6 +389,9 @@ class UNet2DConditionModel(nn.Module):
             if isinstance(m, Attention):
                 m.drop_fused()
                 (m.fused_kv_weight() if m.is_cross else m.fused_qkv_weight())
+        for m in self.modules():      # after the fused q|k|v weights exist: fold the LayerNorms into their consumers
+            if isinstance(m, BasicTransformerBlock):
+                m.finalize()
         self._w_temb = torch.cat(ws, 0).contiguous()
         self._b_temb = torch.cat(bs, 0).contiguous()
         # the 4-channel ends run on the tensor-core GEMM: conv_in weight flattened [320, 36] -> [320, 64] (zero pad);

@@ -38,7 +38,13 @@ def _check_sdxl_case(attn, hidden_states, attention_mask):
 
 
 class AttnProcessor2_0(torch.nn.Module):
-    """Self-attention (and plain cross-attention) processor -- reference AttnProcessor2_0 (:244-332)."""
+    """Self-attention (and plain cross-attention) processor -- reference AttnProcessor2_0 (:244-332).
+
+    Native extensions (keyword-only, used by imagharmony_b200.unet): `residual=` fuses the block's h + attn(...),
+    `ln_stats=` means `hidden_states` are the RAW block input whose LayerNorm is folded into the q|k|v GEMM,
+    `stats_out=` receives the row statistics of the output for the next folded LayerNorm."""
+
+    supports_fused = True
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
@@ -46,21 +52,31 @@ class AttnProcessor2_0(torch.nn.Module):
             raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
-                 *args, residual: Optional[torch.Tensor] = None, **kwargs):
+                 *args, residual: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
+                 ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None, **kwargs):
         _check_sdxl_case(attn, hidden_states, attention_mask)
         B, N, C = hidden_states.shape
         H = attn.heads
         x = hidden_states.reshape(B * N, C)
         if encoder_hidden_states is None:
-            qkv = ops.linear(x, attn.fused_qkv_weight())                          # to_q | to_k | to_v in one GEMM
+            if ln_stats is not None:
+                w_g, ln_s, ln_c = attn._ln
+                qkv = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))       # LayerNorm folded into q|k|v
+            else:
+                qkv = ops.linear(x, attn.fused_qkv_weight())                      # to_q | to_k | to_v in one GEMM
             o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N)
         else:
             Nk = encoder_hidden_states.shape[1]
-            q = ops.linear(x, attn.to_q.weight)
+            if ln_stats is not None:
+                w_g, ln_s, ln_c = attn._ln
+                q = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))
+            else:
+                q = ops.linear(x, attn.to_q.weight)
             kv = ops.linear(encoder_hidden_states.reshape(B * Nk, -1), attn.fused_kv_weight())
             o = ops.attention(q, kv[:, :C], kv[:, C:], B, H, N, Nk)
         res2d = None if residual is None else residual.reshape(B * N, C)
-        out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d)   # :320 (+ fused h + ...)
+        out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d,
+                         stats_out=stats_out)                                     # :320 (+ fused h + ...)
         return out.reshape(B, N, C)
 
 
@@ -69,7 +85,10 @@ class IPAttnProcessor2_0(torch.nn.Module):
 
     Owns `to_k_ip.weight` / `to_v_ip.weight` [hidden, cross_dim] (no bias, :361-362); public mutable attributes
     `scale`, `skip`, `num_tokens` exactly like the reference (set_scale mutates `scale`, ip_adapter.py:179-182).
+    Native keyword extensions as in AttnProcessor2_0 (residual=, ln_stats=, ln_eps=, stats_out=).
     """
+
+    supports_fused = True
 
     def __init__(self, hidden_size, cross_attention_dim=None, scale=1.0, num_tokens=4, skip=False):
         super().__init__()
@@ -128,7 +147,8 @@ class IPAttnProcessor2_0(torch.nn.Module):
         return self._kv
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
-                 residual: Optional[torch.Tensor] = None):
+                 residual: Optional[torch.Tensor] = None, ln_stats: Optional[torch.Tensor] = None,
+                 ln_eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None):
         _check_sdxl_case(attn, hidden_states, attention_mask)
         if encoder_hidden_states is None:
             raise IHError("IPAttnProcessor2_0 needs encoder_hidden_states (it is installed on attn2 only)")
@@ -138,7 +158,11 @@ class IPAttnProcessor2_0(torch.nn.Module):
             cached = self.prepare(attn, encoder_hidden_states)
         _, kv, Nk, n_ip = cached
         x = hidden_states.reshape(B * N, C)
-        q = ops.linear(x, attn.to_q.weight)                                       # :396
+        if ln_stats is not None:
+            w_g, ln_s, ln_c = attn._ln
+            q = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))             # norm2 folded into to_q (:396)
+        else:
+            q = ops.linear(x, attn.to_q.weight)                                   # :396
         o = ops.attention(q, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip,
                           ip_scale=float(self.scale))                             # :423-450
         if self.keep_attn_map and not self.skip:
@@ -146,7 +170,7 @@ class IPAttnProcessor2_0(torch.nn.Module):
             qh = q.reshape(B, N, attn.heads, 64).permute(0, 2, 1, 3)
             self.attn_map = qh @ k_ip.transpose(-2, -1).softmax(dim=-1)           # :443-444 (diagnostic only)
         res2d = None if residual is None else residual.reshape(B * N, C)
-        out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d)   # :453
+        out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d, stats_out=stats_out)   # :453
         return out.reshape(B, N, C)
 
 

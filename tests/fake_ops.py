@@ -21,11 +21,28 @@ def _f(t):
     return None if t is None else t.float()
 
 
+def fold_layernorm(w, bias, gamma, beta):
+    w_g = (w.float() * gamma.float()[None, :]).to(w.dtype).contiguous()
+    ln_s = w_g.float().sum(dim=1)
+    ln_c = w.float() @ beta.float()
+    if bias is not None:
+        ln_c = ln_c + bias.float()
+    return w_g, ln_s, ln_c
+
+
 def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, gelu=False,
-           out=None, tile_n=0):
+           out=None, tile_n=0, ln=None, stats_out=None):
     _count[0] += 1
     y = x.float() @ w.float().t()
-    if bias is not None:
+    if ln is not None:
+        st, ln_s, ln_c, eps = ln
+        K = x.shape[1]
+        tot = st.float().sum(dim=1)
+        mean = tot[:, 0] / K
+        var = (tot[:, 1] / K - mean * mean).clamp_min(0)
+        rstd = torch.rsqrt(var + eps)
+        y = rstd[:, None] * (y - mean[:, None] * ln_s.float()[None, :]) + ln_c.float()[None, :]
+    elif bias is not None:
         y = y + bias.float()
     if geglu:
         a, g = y.chunk(2, dim=-1)
@@ -39,6 +56,12 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
     if residual is not None:
         y = y + residual.float()
     y = y.to(x.dtype)
+    if stats_out is not None:
+        yf = y.float()
+        n = yf.shape[1]
+        pad = (-n) % 64
+        yp = F.pad(yf, (0, pad)).reshape(yf.shape[0], -1, 64)
+        stats_out.copy_(torch.stack([yp.sum(-1), (yp * yp).sum(-1)], dim=-1))
     if out is not None:
         out.copy_(y)
         return out

@@ -100,6 +100,41 @@ def test_gemm_geglu(ops, M, C, tile_n):
     check(out, a * F.gelu(g), f"geglu {M}x{C}")
 
 
+@pytest.mark.parametrize("M,N,K,geglu,tile_n", [
+    (2048, 3840, 1280, False, 0),     # norm1 -> q|k|v
+    (2048, 1280, 1280, False, 192),
+    (8192, 640, 640, False, 0),       # norm2 -> to_q at the 640-channel level
+    (2048, 5120, 1280, True, 0),      # norm3 -> GEGLU projection
+    (1000, 2560, 640, True, 512),     # CTA pair, ragged M
+])
+def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
+    """producer GEMM writes per-row (sum, sumsq) slabs; the consumer applies LayerNorm algebraically in its epilogue."""
+    a = rnd(M, K, seed=31)
+    wp = rnd(K, K, scale=K ** -0.5, seed=32)
+    bp = rnd(K, seed=33)
+    res = rnd(M, K, seed=34) * 2 + 0.5            # non-zero mean rows
+    stats = torch.full((M, (K + 63) // 64, 2), float("nan"), dtype=torch.float32, device="cuda")
+    h = ops.linear(a, wp, bp, residual=res, stats_out=stats)
+    hf = h.float()
+    # the statistics are those of the ROUNDED fp16 output rows
+    s = stats.sum(dim=1)
+    torch.testing.assert_close(s[:, 0], hf.sum(dim=1), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(s[:, 1], (hf * hf).sum(dim=1), rtol=1e-5, atol=1e-3)
+
+    gamma = (1 + 0.2 * rnd(K, seed=35).float()).half()
+    beta = (0.1 * rnd(K, seed=36).float()).half()
+    rows = 2 * N if geglu else N
+    w = rnd(rows, K, scale=K ** -0.5, seed=37)
+    b = rnd(rows, seed=38)
+    w_g, ln_s, ln_c = ops.fold_layernorm(w, b, gamma, beta)
+    out = ops.linear(h, w_g, geglu=geglu, ln=(stats, ln_s, ln_c, 1e-5), tile_n=tile_n)
+    n = F.layer_norm(hf, (K,), gamma.float(), beta.float(), 1e-5)
+    y = n @ w.float().t() + b.float()
+    ref = y[:, :N] * F.gelu(y[:, N:]) if geglu else y
+    # the folded path rounds w*gamma to fp16 instead of rounding LN(x): allow 2e-3
+    check(out, ref, f"ln_fold M{M} N{N} K{K} geglu{geglu}", rtol=2e-3, atol=2e-3)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # conv 3x3
 # ------------------------------------------------------------------------------------------------------------
