@@ -28,7 +28,7 @@ SIGNATURES = {
                             c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ih_gemm_ln_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p,
                                c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
-                               c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+                               c_float, c_void_p, c_void_p]),
     "ih_gemm_set_trace": (None, [c_void_p]),
     "ih_conv2d_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

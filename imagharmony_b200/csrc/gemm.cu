@@ -54,15 +54,14 @@ struct GemmParams {
   int act;  // 0 none, 1 SiLU, 2 GELU(erf) (applied after bias, before residual)
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA 0 (ih_gemm_set_trace), nullptr in production
   // LayerNorm folding (plain GEMM mode only).  A producer GEMM writes, per output row and 64-column slab, the sum and
-  // the sum of squares of the fp16-rounded values it stores (stats_out [M, ceil(N/64), 2] fp32, one writer per slot:
-  // deterministic, nothing to zero).  The consumer GEMM multiplies the RAW rows with gamma-scaled weights and applies
-  //   out = rstd[m] * (acc - mean[m] * ln_s[n]) + ln_c[n]     (= LayerNorm(x) W^T + b exactly, in real arithmetic)
-  // with mean / rstd rebuilt from the producer's slabs (ln_stats [M, ln_slabs, 2]).
+  // the sum of squares of the fp16-rounded values it stores (stats_out [ceil(N/64), M, 2] fp32, one writer per slot:
+  // deterministic, nothing to zero).  The consumer GEMM multiplies the RAW rows with gamma-scaled, row-CENTRED weights
+  // Wc[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma) -- so x Wc^T = (x - mean(x)) (W gamma)^T -- and applies
+  //   out = rstd[m] * acc + c[n],  c = W beta + b (passed as `bias`)   (= LayerNorm(x) W^T + b in real arithmetic)
+  // with rstd rebuilt from the producer's slabs (ln_stats [ln_slabs, M, 2]).
   float* stats_out;
   const float* ln_stats;
   int ln_slabs;
-  const float* ln_s;
-  const float* ln_c;
   float ln_inv_c;
   float ln_eps;
 };
@@ -300,16 +299,22 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         rb = p.rowbias + grp * p.ld_rowbias;
       }
 
-      float ln_mean = 0.f, ln_rstd = 1.f;
+      float ln_rstd = 1.f;
       if (p.ln_stats && tile_live && orow < p.M) {   // hidden behind the main loop of this tile
-        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow * p.ln_slabs;
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow;   // [slab][row]: coalesced over rows
         float ssum = 0.f, ssq = 0.f;
-        for (int i = 0; i < p.ln_slabs; ++i) {
-          const float2 v2 = st[i];
-          ssum += v2.x;
-          ssq += v2.y;
+        for (int i0 = 0; i0 < p.ln_slabs; i0 += 10) {   // 10 independent loads in flight: one L2 round trip per 640 features
+          float2 t[10];
+#pragma unroll
+          for (int i = 0; i < 10; ++i)
+            t[i] = (i0 + i < p.ln_slabs) ? __ldg(st + (long long)(i0 + i) * p.M) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            ssum += t[i].x;
+            ssq += t[i].y;
+          }
         }
-        ln_mean = ssum * p.ln_inv_c;
+        const float ln_mean = ssum * p.ln_inv_c;
         const float var = fmaxf(ssq * p.ln_inv_c - ln_mean * ln_mean, 0.f);
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
@@ -343,9 +348,22 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         for (int h32 = 0; h32 < 2; ++h32) {
           uint32_t v[32];
           uint32_t g[32];
+          // bias / gate-bias / row-bias vectors of 8 columns, fetched one j-step ahead of their use so that their L1 / L2
+          // latency overlaps the TMEM load (first step) or the arithmetic of the previous step.  Columns past N are
+          // clipped by the TMA store, so a clamped (in-range) address is good enough for them.
+          auto fetch = [&](int j, uint4& bv, uint4& gv, uint4& rv) {
+            int col = col0 + j * 8;
+            if (col > p.N - 8) col = p.N - 8;
+            bv = gv = rv = make_uint4(0u, 0u, 0u, 0u);
+            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            if (GEGLU && p.bias) gv = __ldg(reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col));
+            if (rb) rv = __ldg(reinterpret_cast<const uint4*>(rb + col));
+          };
+          uint4 bv, gv, rv;
           if (live) {
             tmem_ld_32x32b_x32(taddr + sl * 64 + h32 * 32, v);
             if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64 + h32 * 32, g);
+            fetch(h32 * 4, bv, gv, rv);
             tmem_ld_wait();
           }
           if (sl == last_slab && h32 == 1) {
@@ -362,66 +380,46 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const int j = h32 * 4 + j4;
-              const int col = col0 + j * 8;
+              const bool col_ok = col0 + j * 8 < p.N;
+              uint4 nbv, ngv, nrv;
+              if (j4 < 3) fetch(j + 1, nbv, ngv, nrv);
               float x[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j4 * 8 + e]);
-              const bool col_ok = col < p.N;   // columns past N are clipped by the store; skip their bias loads
-              if (p.ln_stats && col_ok) {
-                const float4 s0 = *reinterpret_cast<const float4*>(p.ln_s + col);
-                const float4 s1 = *reinterpret_cast<const float4*>(p.ln_s + col + 4);
-                const float4 c0 = *reinterpret_cast<const float4*>(p.ln_c + col);
-                const float4 c1 = *reinterpret_cast<const float4*>(p.ln_c + col + 4);
-                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaf(ln_rstd, x[e] - ln_mean * sv[e], cv[e]);
-              } else if (p.bias && col_ok) {
-                const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + col);
-                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+              {
+                // acc * rstd + bias: rstd = 1 without a folded LayerNorm; with one, `bias` carries W beta + b and the
+                // weight rows are gamma-scaled AND centred, so the mean term has already cancelled inside the MMA
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 f = unpack_half2(bw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
+                  x[2 * e] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e]), f.x);
+                  x[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e + 1]), f.y);
                 }
               }
               if (GEGLU) {
                 float gt[8];
+                const uint32_t bw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) gt[e] = __uint_as_float(g[j4 * 8 + e]);
-                if (p.ln_stats && col_ok) {
-                  const int gc = p.gate_row_off + col;
-                  const float4 s0 = *reinterpret_cast<const float4*>(p.ln_s + gc);
-                  const float4 s1 = *reinterpret_cast<const float4*>(p.ln_s + gc + 4);
-                  const float4 c0 = *reinterpret_cast<const float4*>(p.ln_c + gc);
-                  const float4 c1 = *reinterpret_cast<const float4*>(p.ln_c + gc + 4);
-                  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                  const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) gt[e] = fmaf(ln_rstd, gt[e] - ln_mean * sv[e], cv[e]);
-                } else if (p.bias && col_ok) {
-                  const uint4 b4 = *reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col);
-                  const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = unpack_half2(bw[e]);
-                    gt[2 * e] += f.x;
-                    gt[2 * e + 1] += f.y;
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_half2(bw[e]);
+                  gt[2 * e] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e]), f.x);
+                  gt[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e + 1]), f.y);
                 }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
               }
-              if (rb && col_ok) {
-                const uint4 b4 = *reinterpret_cast<const uint4*>(rb + col);
-                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+              {
+                const uint32_t bw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 f = unpack_half2(bw[e]);
                   x[2 * e] += f.x;
                   x[2 * e + 1] += f.y;
                 }
+              }
+              if (j4 < 3) {
+                bv = nbv;
+                gv = ngv;
+                rv = nrv;
               }
               if (p.act == 1) {
 #pragma unroll
@@ -460,7 +458,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           }
         }
         if (live && p.stats_out && orow < p.M)
-          reinterpret_cast<float2*>(p.stats_out)[orow * ((p.N + 63) >> 6) + (col0 >> 6)] = make_float2(st_sum, st_sq);
+          reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
         if (live) {
           fence_proxy_async_smem();
           named_bar_sync(1 + half, 128);
@@ -619,14 +617,13 @@ extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const vo
                            int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                            long long ldo, int M, int N, int K, int epilogue, int tile_n, void* stream) {
   return ih_gemm_ln_f16(a, lda, w, bias, rowbias, rows_per_group, ld_rowbias, residual, ldr, out, ldo, M, N, K, epilogue,
-                        tile_n, nullptr, 0, nullptr, nullptr, 0.f, nullptr, stream);
+                        tile_n, nullptr, 0, 0.f, nullptr, stream);
 }
 
 extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                               int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                               long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats,
-                              int ln_slabs, const void* ln_s, const void* ln_c, float ln_eps, void* stats_out,
-                              void* stream) {
+                              int ln_slabs, float ln_eps, void* stats_out, void* stream) {
   IH_CHECK(a && w && out, IH_ERR_ARG, "ih_gemm_f16: null pointer");
   IH_CHECK(M > 0 && N > 0 && K > 0, IH_ERR_SHAPE, "ih_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
   IH_CHECK(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, IH_ERR_ALIGN,
@@ -661,13 +658,11 @@ extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const
   p.ldo = ldo;
   p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : 0);
   p.trace = g_trace;
-  IH_CHECK(!ln_stats || (ln_s && ln_c && ln_slabs > 0), IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_s, ln_c, ln_slabs");
+  IH_CHECK(!ln_stats || ln_slabs > 0, IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_slabs > 0");
   IH_CHECK(!stats_out || N % 64 == 0 || geglu, IH_ERR_SHAPE, "ih_gemm_ln_f16: stats_out needs N %% 64 == 0");
   p.stats_out = (float*)stats_out;
   p.ln_stats = (const float*)ln_stats;
   p.ln_slabs = ln_slabs;
-  p.ln_s = (const float*)ln_s;
-  p.ln_c = (const float*)ln_c;
   p.ln_inv_c = 1.0f / (float)K;
   p.ln_eps = ln_eps;
   const int m_tiles = (M + BM - 1) / BM;

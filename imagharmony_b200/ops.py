@@ -53,9 +53,9 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epi(x @ w.T + bias + rowbias[row // rows_per_group]) + residual ; x [M,K], w [N,K] (nn.Linear layout).
 
-    LayerNorm folding: `stats_out` (float32 [M, ceil(N/64), 2]) receives per-row / per-64-column (sum, sumsq) of the
-    stored values; `ln=(stats, ln_s, ln_c, eps)` makes this GEMM consume RAW rows `x` with a gamma-scaled weight and apply
-    rstd * (acc - mean * ln_s) + ln_c in the epilogue (see fold_layernorm)."""
+    LayerNorm folding: `stats_out` (float32 [ceil(N/64), M, 2]) receives per-row / per-64-column (sum, sumsq) of the
+    stored values; `ln=(stats, eps)` makes this GEMM consume RAW rows `x` with the gamma-scaled, row-centred weight and
+    the constant vector of fold_layernorm (passed as `w`, `bias`) and apply rstd * acc + bias in the epilogue."""
     lib = _lib.load()
     _req(x, "x"); _req(w, "w")
     M, K = x.shape
@@ -73,34 +73,38 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                              _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _stream())
         check(rc, "ih_gemm_f16")
         return out
-    ln_stats = ln_s = ln_c = None
+    ln_stats = None
     ln_slabs, ln_eps = 0, 0.0
     if ln is not None:
-        ln_stats, ln_s, ln_c, ln_eps = ln
-        _req(ln_stats, "ln_stats", torch.float32); _req(ln_s, "ln_s", torch.float32); _req(ln_c, "ln_c", torch.float32)
-        if ln_stats.shape[0] != M or ln_stats.shape[-1] != 2 or not ln_stats.is_contiguous() or ln_s.numel() != N:
-            raise IHError("linear: ln statistics must be contiguous [M, slabs, 2] and ln_s/ln_c [N]")
-        ln_slabs = ln_stats.shape[1]
+        ln_stats, ln_eps = ln
+        _req(ln_stats, "ln_stats", torch.float32)
+        if ln_stats.dim() != 3 or ln_stats.shape[1] != M or ln_stats.shape[-1] != 2 or not ln_stats.is_contiguous():
+            raise IHError("linear: ln statistics must be contiguous [slabs, M, 2]")
+        if ln_stats.shape[0] != (K + 63) // 64:
+            raise IHError(f"linear: ln statistics cover {ln_stats.shape[0]} slabs, K={K} needs {(K + 63) // 64}")
+        ln_slabs = ln_stats.shape[0]
     if stats_out is not None:
         _req(stats_out, "stats_out", torch.float32)
-        if tuple(stats_out.shape) != (M, (n_out + 63) // 64, 2) or not stats_out.is_contiguous():
-            raise IHError(f"linear: stats_out must be contiguous float32 [{M}, {(n_out + 63) // 64}, 2]")
+        if tuple(stats_out.shape) != ((n_out + 63) // 64, M, 2) or not stats_out.is_contiguous():
+            raise IHError(f"linear: stats_out must be contiguous float32 [{(n_out + 63) // 64}, {M}, 2]")
     rc = lib.ih_gemm_ln_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(rowbias), rows_per_group, ldrb,
                             _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _p(ln_stats),
-                            ln_slabs, _p(ln_s), _p(ln_c), float(ln_eps), _p(stats_out), _stream())
+                            ln_slabs, float(ln_eps), _p(stats_out), _stream())
     check(rc, "ih_gemm_ln_f16")
     return out
 
 
 def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
-    """LayerNorm(x) @ w.T + bias == rstd * (x @ w_g.T - mean * ln_s) + ln_c with
-       w_g = w * gamma (fp16), ln_s[n] = sum_k w_g[n, k], ln_c[n] = sum_k beta[k] * w[n, k] + bias[n]  (fp32)."""
-    w_g = (w.float() * gamma.float()[None, :]).to(torch.float16).contiguous()
-    ln_s = w_g.float().sum(dim=1).contiguous()
-    ln_c = w.float() @ beta.float()
+    """LayerNorm(x) @ w.T + bias == rstd(x) * (x @ w_c.T) + c with
+       w_c[n, k] = w[n, k] gamma[k] - mean_k(w[n, :] gamma)   (rows centred: x @ w_c.T = (x - mean(x)) @ (w gamma).T)
+       c[n]      = sum_k beta[k] w[n, k] + bias[n].
+    Returns (w_c, c) in fp16 for ops.linear(x_raw, w_c, c, ln=(row statistics of x_raw, eps))."""
+    w_g = w.double() * gamma.double()[None, :]
+    w_c = (w_g - w_g.mean(dim=1, keepdim=True)).to(torch.float16).contiguous()
+    c = w.double() @ beta.double()
     if bias is not None:
-        ln_c = ln_c + bias.float()
-    return w_g, ln_s, ln_c.contiguous()
+        c = c + bias.double()
+    return w_c, c.to(torch.float16).contiguous()
 
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,

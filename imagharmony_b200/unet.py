@@ -46,7 +46,7 @@ class Attention(nn.Module):
         self.processor = None
         self._w_qkv = None
         self._w_kv = None
-        self._ln = None      # (gamma-scaled weight, ln_s, ln_c) of the projection that consumes a folded LayerNorm
+        self._ln = None      # (gamma-scaled centred weight, constant vector) of the projection that consumes a folded LayerNorm
 
     def fold_ln(self, norm: nn.LayerNorm) -> None:
         """Fold the block's LayerNorm into the first projection of this attention (q|k|v for attn1, q for attn2)."""
@@ -151,7 +151,7 @@ class BasicTransformerBlock(nn.Module):
             n = ops.layernorm(h, norm.weight, norm.bias, norm.eps)
             out = proc(attn, n, encoder_hidden_states=ehs, attention_mask=None)
             return ops.add_bcast(h, out.contiguous()), None
-        st = torch.empty((B * N, C // 64, 2), dtype=torch.float32, device=h.device) if want_stats else None
+        st = torch.empty((C // 64, B * N, 2), dtype=torch.float32, device=h.device) if want_stats else None
         if h_stats is not None and attn._ln is not None:
             return attn(h, ehs, residual=h, ln_stats=h_stats, ln_eps=norm.eps, stats_out=st), st
         n = ops.layernorm(h, norm.weight, norm.bias, norm.eps)
@@ -165,12 +165,12 @@ class BasicTransformerBlock(nn.Module):
         h, st = self._attend(self.attn2, self.norm2, h, ehs, st, fold)
         h2d = h.reshape(B * N, C)
         if st is not None and self._ln_ff is not None:
-            w_g, ln_s, ln_c = self._ln_ff
-            g = ops.linear(h2d, w_g, geglu=True, ln=(st, ln_s, ln_c, self.norm3.eps))
+            w_c, c = self._ln_ff
+            g = ops.linear(h2d, w_c, c, geglu=True, ln=(st, self.norm3.eps))
         else:
             n = ops.layernorm(h, self.norm3.weight, self.norm3.bias, self.norm3.eps)
             g = ops.linear(n.reshape(B * N, C), self.ff.net[0].proj.weight, self.ff.net[0].proj.bias, geglu=True)
-        st_out = torch.empty((B * N, C // 64, 2), dtype=torch.float32, device=h.device) if (fold and want_stats) else None
+        st_out = torch.empty((C // 64, B * N, 2), dtype=torch.float32, device=h.device) if (fold and want_stats) else None
         h2 = ops.linear(g, self.ff.net[2].weight, self.ff.net[2].bias, residual=h2d, stats_out=st_out)
         return h2.reshape(B, N, C), st_out
 
@@ -187,7 +187,7 @@ class Transformer2DModel(nn.Module):
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
         h = ops.groupnorm(x, self.norm.weight, self.norm.bias, groups=self.groups, eps=1e-6, silu=False)
-        st = torch.empty((B * H * W, C // 64, 2), dtype=torch.float32, device=x.device) if C % 64 == 0 else None
+        st = torch.empty((C // 64, B * H * W, 2), dtype=torch.float32, device=x.device) if C % 64 == 0 else None
         h = ops.linear(h.reshape(B * H * W, C), self.proj_in.weight, self.proj_in.bias, stats_out=st)
         h = h.reshape(B, H * W, C)
         nblk = len(self.transformer_blocks)

@@ -41,15 +41,16 @@ int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, c
 
 /* ih_gemm_f16 with LayerNorm folded in (BasicTransformerBlock norm1/2/3 -> attn / FF projections).
  *   stats_out != NULL : additionally write, per output row and 64-column slab, (sum, sum of squares) of the fp16 values
- *                       stored: float [M, ceil(N/64), 2] (one writer per slot; deterministic).
- *   ln_stats  != NULL : `a` holds the RAW (un-normalised) rows, `w` the weight pre-multiplied by the LayerNorm gamma,
- *                       ln_s[n] = sum_k w[n,k] (fp32), ln_c[n] = sum_k beta[k] W[n,k] + bias[n] (fp32); the epilogue
- *                       applies out = rstd[m] * (acc - mean[m] * ln_s[n]) + ln_c[n], mean / rstd rebuilt from the
- *                       producer's slabs ln_stats [M, ln_slabs, 2] over K features with epsilon ln_eps; `bias` ignored. */
+ *                       stored: float [ceil(N/64), M, 2] (one writer per slot; deterministic).
+ *   ln_stats  != NULL : `a` holds the RAW (un-normalised) rows; `w` is the weight pre-multiplied by the LayerNorm gamma
+ *                       with every row centred (w[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma)), so that
+ *                       a w^T = (a - mean(a)) (W gamma)^T; `bias` = W beta + b.  The epilogue applies
+ *                       out = rstd[m] * acc + bias[n], rstd rebuilt from the producer's slabs
+ *                       ln_stats [ln_slabs, M, 2] over the K features with epsilon ln_eps. */
 int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                    int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                    long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats, int ln_slabs,
-                   const void* ln_s, const void* ln_c, float ln_eps, void* stats_out, void* stream);
+                   float ln_eps, void* stats_out, void* stream);
 
 /* Debug aid: CTA 0 of later GEMM / conv launches writes %globaltimer stamps into this device buffer (>= 16 uint64);
  * NULL disables.  Not used on the product path. */

@@ -60,16 +60,16 @@ class AttnProcessor2_0(torch.nn.Module):
         x = hidden_states.reshape(B * N, C)
         if encoder_hidden_states is None:
             if ln_stats is not None:
-                w_g, ln_s, ln_c = attn._ln
-                qkv = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))       # LayerNorm folded into q|k|v
+                w_c, c = attn._ln
+                qkv = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))                # LayerNorm folded into q|k|v
             else:
                 qkv = ops.linear(x, attn.fused_qkv_weight())                      # to_q | to_k | to_v in one GEMM
             o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N)
         else:
             Nk = encoder_hidden_states.shape[1]
             if ln_stats is not None:
-                w_g, ln_s, ln_c = attn._ln
-                q = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))
+                w_c, c = attn._ln
+                q = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))
             else:
                 q = ops.linear(x, attn.to_q.weight)
             kv = ops.linear(encoder_hidden_states.reshape(B * Nk, -1), attn.fused_kv_weight())
@@ -159,8 +159,8 @@ class IPAttnProcessor2_0(torch.nn.Module):
         _, kv, Nk, n_ip = cached
         x = hidden_states.reshape(B * N, C)
         if ln_stats is not None:
-            w_g, ln_s, ln_c = attn._ln
-            q = ops.linear(x, w_g, ln=(ln_stats, ln_s, ln_c, ln_eps))             # norm2 folded into to_q (:396)
+            w_c, c = attn._ln
+            q = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))                      # norm2 folded into to_q (:396)
         else:
             q = ops.linear(x, attn.to_q.weight)                                   # :396
         o = ops.attention(q, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip,

@@ -22,12 +22,12 @@ def _f(t):
 
 
 def fold_layernorm(w, bias, gamma, beta):
-    w_g = (w.float() * gamma.float()[None, :]).to(w.dtype).contiguous()
-    ln_s = w_g.float().sum(dim=1)
-    ln_c = w.float() @ beta.float()
+    w_g = w.double() * gamma.double()[None, :]
+    w_c = (w_g - w_g.mean(dim=1, keepdim=True)).to(w.dtype).contiguous()
+    c = w.double() @ beta.double()
     if bias is not None:
-        ln_c = ln_c + bias.float()
-    return w_g, ln_s, ln_c
+        c = c + bias.double()
+    return w_c, c.to(w.dtype)
 
 
 def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, gelu=False,
@@ -35,14 +35,13 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
     _count[0] += 1
     y = x.float() @ w.float().t()
     if ln is not None:
-        st, ln_s, ln_c, eps = ln
+        st, eps = ln
         K = x.shape[1]
-        tot = st.float().sum(dim=1)
+        tot = st.float().sum(dim=0)
         mean = tot[:, 0] / K
         var = (tot[:, 1] / K - mean * mean).clamp_min(0)
-        rstd = torch.rsqrt(var + eps)
-        y = rstd[:, None] * (y - mean[:, None] * ln_s.float()[None, :]) + ln_c.float()[None, :]
-    elif bias is not None:
+        y = torch.rsqrt(var + eps)[:, None] * y
+    if bias is not None:
         y = y + bias.float()
     if geglu:
         a, g = y.chunk(2, dim=-1)
@@ -61,7 +60,7 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
         n = yf.shape[1]
         pad = (-n) % 64
         yp = F.pad(yf, (0, pad)).reshape(yf.shape[0], -1, 64)
-        stats_out.copy_(torch.stack([yp.sum(-1), (yp * yp).sum(-1)], dim=-1))
+        stats_out.copy_(torch.stack([yp.sum(-1), (yp * yp).sum(-1)], dim=-1).transpose(0, 1))
     if out is not None:
         out.copy_(y)
         return out

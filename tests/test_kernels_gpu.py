@@ -113,11 +113,11 @@ def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
     wp = rnd(K, K, scale=K ** -0.5, seed=32)
     bp = rnd(K, seed=33)
     res = rnd(M, K, seed=34) * 2 + 0.5            # non-zero mean rows
-    stats = torch.full((M, (K + 63) // 64, 2), float("nan"), dtype=torch.float32, device="cuda")
+    stats = torch.full(((K + 63) // 64, M, 2), float("nan"), dtype=torch.float32, device="cuda")
     h = ops.linear(a, wp, bp, residual=res, stats_out=stats)
     hf = h.float()
     # the statistics are those of the ROUNDED fp16 output rows
-    s = stats.sum(dim=1)
+    s = stats.sum(dim=0)
     torch.testing.assert_close(s[:, 0], hf.sum(dim=1), rtol=1e-5, atol=1e-3)
     torch.testing.assert_close(s[:, 1], (hf * hf).sum(dim=1), rtol=1e-5, atol=1e-3)
 
@@ -126,13 +126,23 @@ def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
     rows = 2 * N if geglu else N
     w = rnd(rows, K, scale=K ** -0.5, seed=37)
     b = rnd(rows, seed=38)
-    w_g, ln_s, ln_c = ops.fold_layernorm(w, b, gamma, beta)
-    out = ops.linear(h, w_g, geglu=geglu, ln=(stats, ln_s, ln_c, 1e-5), tile_n=tile_n)
-    n = F.layer_norm(hf, (K,), gamma.float(), beta.float(), 1e-5)
-    y = n @ w.float().t() + b.float()
-    ref = y[:, :N] * F.gelu(y[:, N:]) if geglu else y
-    # the folded path rounds w*gamma to fp16 instead of rounding LN(x): allow 2e-3
-    check(out, ref, f"ln_fold M{M} N{N} K{K} geglu{geglu}", rtol=2e-3, atol=2e-3)
+    w_c, c = ops.fold_layernorm(w, b, gamma, beta)
+    out = ops.linear(h, w_c, c, geglu=geglu, ln=(stats, 1e-5), tile_n=tile_n)
+    # exact (fp64) result, and the unfused kernel pipeline (explicit LayerNorm kernel -> GEMM) the fold replaces
+    n64 = F.layer_norm(h.double(), (K,), gamma.double(), beta.double(), 1e-5)
+    y = n64 @ w.double().t() + b.double()
+    exact = (y[:, :N] * F.gelu(y[:, N:]) if geglu else y).float()
+    unfused = ops.linear(ops.layernorm(h, gamma, beta, 1e-5), w, b, geglu=geglu).float()
+    e_fold, e_unf = (out.float() - exact).abs(), (unfused - exact).abs()
+    rms_fold, rms_unf = e_fold.pow(2).mean().sqrt().item(), e_unf.pow(2).mean().sqrt().item()
+    print(f"[ln_fold M{M} N{N} K{K} geglu{geglu}] rms err fold {rms_fold:.3e} unfused {rms_unf:.3e}; "
+          f"max fold {e_fold.max().item():.3e} unfused {e_unf.max().item():.3e}")
+    # the fold moves one fp16 rounding from LN(x) to W*gamma: it must be as accurate as the pipeline it replaces
+    assert torch.isfinite(out).all()
+    assert rms_fold <= 1.25 * rms_unf + 1e-6, (rms_fold, rms_unf)
+    assert e_fold.max().item() <= 2.0 * e_unf.max().item() + 1e-3
+    if not geglu:
+        check(out, exact, f"ln_fold M{M} N{N} K{K}", rtol=2e-3, atol=2e-3)
 
 
 # ------------------------------------------------------------------------------------------------------------
