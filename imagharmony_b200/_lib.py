@@ -34,6 +34,10 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ih_attention_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                  c_longlong, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ih_attention_ws_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                    c_longlong, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_longlong,
+                                    c_void_p]),
+    "ih_attention_workspace_bytes": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
     "ih_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_float, c_int, c_void_p]),
     "ih_groupnorm_workspace_bytes": (c_longlong, [c_int, c_int]),

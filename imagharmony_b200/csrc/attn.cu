@@ -32,6 +32,12 @@ struct AttnParams {
   float ip_scale;
   __half* out;
   long long ldo;
+  // attn2 only: work decomposition.  CTAs [0, n_whole) process a whole (batch, head, 256-query pair); CTA
+  // n_whole + i processes KV part (i % split) of pair n_whole + i / split and writes an un-normalised partial result
+  // (fp32 O rows, running max, running sum) to the workspace, merged by attn_combine_kernel.
+  int H, qpairs, n_whole, split;
+  float* ws_o;   // [slots][256][64]
+  float* ws_ml;  // [slots][256][2]
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -524,10 +530,18 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nb = p.num_kv_blocks;
+  int pair = blockIdx.x, jb = 0, je = p.num_kv_blocks, slot = -1;
+  if (pair >= p.n_whole) {
+    slot = pair - p.n_whole;
+    const int sp = slot / p.split, part = slot - sp * p.split;
+    pair = p.n_whole + sp;
+    jb = part * p.num_kv_blocks / p.split;          // balanced contiguous partition of the KV blocks
+    je = (part + 1) * p.num_kv_blocks / p.split;
+  }
+  const int q0 = (pair % p.qpairs) * 256;
+  const int head = (pair / p.qpairs) % p.H;
+  const int b = pair / (p.qpairs * p.H);
+  const int nb = je - jb;
   const bool tileB_active = (q0 + 128) < p.Nq;
 
   if (warp == 0 && lane == 0) {
@@ -569,10 +583,10 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
       for (int j = 0; j < nb; ++j) {
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], ATT_TILE);
-        tma_load_3d(sK + s * ATT_TILE, &tmK, &k_full[s], head * 64, j * 128, b);
+        tma_load_3d(sK + s * ATT_TILE, &tmK, &k_full[s], head * 64, (jb + j) * 128, b);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], ATT_TILE);
-        tma_load_3d(sV + s * ATT_TILE, &tmV, &v_full[s], head * 64, j * 128, b);
+        tma_load_3d(sV + s * ATT_TILE, &tmV, &v_full[s], head * 64, (jb + j) * 128, b);
         if (++s == A2_KS) {
           s = 0;
           ph ^= 1;
@@ -659,7 +673,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
       for (int j = 0; j < nb; ++j) {
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        const int valid = p.Nk - j * 128;
+        const int valid = p.Nk - (jb + j) * 128;
         // pass 1: row max (two 32-column TMEM loads in flight per wait)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -745,26 +759,51 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
         mbar_arrive(&p_full[t]);
       }
 
-      // epilogue: O / l -> global
+      // epilogue: O / l -> global, or the un-normalised partial (O, m, l) -> workspace for a KV part
       mbar_wait(&o_full[t], 0);
       tc_fence_after();
       const int qrow = q0 + t * 128 + r;
-      const float inv = 1.f / l_run;
-      __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
+      if (slot >= 0) {
+        // the fp32 O tile goes through this tile's (now idle) P buffer and leaves as ONE 32 KiB bulk copy; 16-byte chunk
+        // c of row r sits at chunk position c ^ (r & 15) (bank-conflict-free staging; attn_combine_kernel undoes it)
+        const long long wrow = (long long)slot * 256 + t * 128 + r;
+        uint8_t* stage = sP + t * 2 * ATT_TILE;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld_32x32b_x32(tO + c * 32, ov);
-        tmem_ld_wait();
-        if (qrow < p.Nq) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tO + c * 32, ov);
+          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
-            o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
-            o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
-            o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(stage + r * 256 + (((c * 8 + g) ^ (r & 15)) << 4)) =
+                make_uint4(ov[g * 4 + 0], ov[g * 4 + 1], ov[g * 4 + 2], ov[g * 4 + 3]);
+        }
+        reinterpret_cast<float2*>(p.ws_ml)[wrow] = make_float2(m_used, l_run);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if (q == 0 && lane == 0) {
+          bulk_store_linear(p.ws_o + ((long long)slot * 256 + t * 128) * 64, stage, 2 * ATT_TILE);
+          tma_store_commit();
+          tma_store_wait_all();
+        }
+      } else {
+        const float inv = 1.f / l_run;
+        __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tO + c * 32, ov);
+          tmem_ld_wait();
+          if (qrow < p.Nq) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+              o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+              o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+              o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+            }
           }
         }
       }
@@ -776,13 +815,96 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// Merge the `split` KV parts of the query pairs that attn2_f16_kernel processed piecewise:
+//   M = max_i m_i,  out = sum_i O_i 2^(m_i - M) / sum_i l_i 2^(m_i - M)   (fixed order: deterministic).
+// grid = (#split pairs * 4), block = 256: 64 rows per block, 4 threads (16 columns each) per row.
+__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int sp = blockIdx.x >> 2;
+  const int row = (blockIdx.x & 3) * 64 + (threadIdx.x >> 2);
+  const int c0 = (threadIdx.x & 3) * 16;
+  const int pair = p.n_whole + sp;
+  const int qrow = (pair % p.qpairs) * 256 + row;
+  if (qrow >= p.Nq) return;
+  const int head = (pair / p.qpairs) % p.H;
+  const int b = pair / (p.qpairs * p.H);
+  const float2* ml = reinterpret_cast<const float2*>(p.ws_ml);
+  float mmax = -INFINITY;
+  for (int i = 0; i < p.split; ++i) mmax = fmaxf(mmax, ml[((long long)sp * p.split + i) * 256 + row].x);
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  float l = 0.f;
+  for (int i = 0; i < p.split; ++i) {
+    const long long wrow = ((long long)sp * p.split + i) * 256 + row;
+    const float2 v = ml[wrow];
+    const float w = ex2f(v.x - mmax);
+    l = fmaf(v.y, w, l);
+    const float4* src = reinterpret_cast<const float4*>(p.ws_o + wrow * 64);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 o = src[((c0 >> 2) + g) ^ (row & 15)];   // chunk permutation of the producer's staging
+      acc[g * 4 + 0] = fmaf(o.x, w, acc[g * 4 + 0]);
+      acc[g * 4 + 1] = fmaf(o.y, w, acc[g * 4 + 1]);
+      acc[g * 4 + 2] = fmaf(o.z, w, acc[g * 4 + 2]);
+      acc[g * 4 + 3] = fmaf(o.w, w, acc[g * 4 + 3]);
+    }
+  }
+  const float inv = 1.f / l;
+  __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64 + c0;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint4 o;
+    o.x = pack_half2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv);
+    o.y = pack_half2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv);
+    o.z = pack_half2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv);
+    o.w = pack_half2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv);
+    *reinterpret_cast<uint4*>(dst + g * 8) = o;
+  }
+}
+
+// KV-split plan of the ping-pong kernel: with P query pairs on G SMs (one CTA per SM), the last P mod G pairs would
+// run as a nearly empty extra wave; they are cut into `split` KV parts each so that (P mod G) * split <= G CTAs share
+// that wave.  Returns split (1 = none) and the number of pairs processed whole.
+static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
+  const int G = num_sms();
+  const int rem = pairs % G;
+  *n_whole = pairs;
+  *split = 1;
+  if (rem == 0 || nb < 2) return;
+  int s = G / rem;
+  if (s > nb) s = nb;
+  if (s < 2) return;
+  // measured (tools/attn_probe.py): a KV iteration takes ~2.7 us with every SM busy but ~2.0 us in a sparsely filled
+  // last wave; a part pays ~11 us on top of its iterations (CTA set-up, partial epilogue, merge kernel)
+  const float t_whole = 2.0f * nb, t_split = 2.7f * ((nb + s - 1) / s) + 11.0f;
+  if (t_split >= t_whole) return;
+  *n_whole = pairs - rem;
+  *split = s;
+}
+
 }  // namespace ih
 
 using namespace ih;
 
+extern "C" long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 96 || n_ip != 0) return 0;
+  int n_whole, split;
+  const int pairs = B * H * ((Nq + 255) / 256);
+  attn2_plan(pairs, (Nk + 127) / 128, &n_whole, &split);
+  return (long long)(pairs - n_whole) * split * 256 * (64 + 2) * (long long)sizeof(float);
+}
+
 extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                 long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip,
                                 float ip_scale, void* stream) {
+  return ih_attention_ws_f16(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Nq, Nk, n_ip, ip_scale, nullptr, 0, stream);
+}
+
+extern "C" int ih_attention_ws_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                   long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip,
+                                   float ip_scale, void* workspace, long long workspace_bytes, void* stream) {
   IH_CHECK(q && k && v && out, IH_ERR_ARG, "ih_attention_f16: null pointer");
   IH_CHECK(B > 0 && H > 0 && Nq > 0 && Nk > 0, IH_ERR_SHAPE, "ih_attention_f16: bad shape");
   IH_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, IH_ERR_ALIGN,
@@ -851,8 +973,23 @@ extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, lon
     return 0;
   }
   if (n_ip == 0) {
-    dim3 grid2((Nq + 255) / 256, H, B);
-    IH_CUDA(launch_kernel(attn2_f16_kernel, dim3(grid2), dim3(A2_THREADS), (size_t)(A2_SMEM_BYTES), (cudaStream_t)stream, tq, tk, tv, p));
+    p.H = H;
+    p.qpairs = (Nq + 255) / 256;
+    const int pairs = B * H * p.qpairs;
+    attn2_plan(pairs, p.num_kv_blocks, &p.n_whole, &p.split);
+    const long long slots = (long long)(pairs - p.n_whole) * p.split;
+    if (slots > 0 && (!workspace || workspace_bytes < slots * 256 * 66 * (long long)sizeof(float))) {
+      p.n_whole = pairs;   // no (or too small a) workspace: every pair runs whole
+      p.split = 1;
+    }
+    const int n_split_ctas = (pairs - p.n_whole) * p.split;
+    p.ws_o = (float*)workspace;
+    p.ws_ml = p.ws_o + (long long)n_split_ctas * 256 * 64;
+    IH_CUDA(launch_kernel(attn2_f16_kernel, dim3(p.n_whole + n_split_ctas), dim3(A2_THREADS), (size_t)(A2_SMEM_BYTES),
+                          (cudaStream_t)stream, tq, tk, tv, p));
+    if (n_split_ctas > 0)
+      IH_CUDA(launch_kernel(attn_combine_kernel, dim3((pairs - p.n_whole) * 4), dim3(256), (size_t)0,
+                            (cudaStream_t)stream, p));
     return 0;
   }
   dim3 grid((Nq + 127) / 128, H, B);

@@ -299,6 +299,13 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         rb = p.rowbias + grp * p.ld_rowbias;
       }
 
+      // the residual tile of this half-group's first slab is fetched now, behind the main loop (the staging slab is
+      // free: the previous tile's store has been read out); later slabs must wait for their predecessor's store
+      if (tile_live && p.residual && half < SLABS && n0 + half * 64 < p.N && elected) {
+        mbar_arrive_expect_tx(&res_bar[half], BM * 128);
+        if (p.mode == 0) tma_load_2d(my_stg, &rmap, &res_bar[half], n0 + half * 64, m_tile * BM);
+        else tma_load_4d(my_stg, &rmap, &res_bar[half], n0 + half * 64, x0, y0, img);
+      }
       float ln_rstd = 1.f;
       if (p.ln_stats && tile_live && orow < p.M) {   // hidden behind the main loop of this tile
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow;   // [slab][row]: coalesced over rows
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       for (int sl = half; sl < SLABS; sl += 2) {
         const int col0 = n0 + sl * 64;
         const bool live = tile_live && (col0 < p.N);   // uniform over the half-group
-        if (live && p.residual) {
+        if (live && p.residual && sl != half) {
           if (elected) {
             mbar_arrive_expect_tx(&res_bar[half], BM * 128);
             if (p.mode == 0) tma_load_2d(my_stg, &rmap, &res_bar[half], col0, m_tile * BM);

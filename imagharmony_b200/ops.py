@@ -136,16 +136,36 @@ def pack_conv3x3_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     return w_oihw.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
 
 
+_attn_ws = {}
+
+
+def _attn_workspace(device, need: int) -> Optional[torch.Tensor]:
+    """Persistent scratch for the KV-split self-attention parts (one per device; calls are stream-ordered)."""
+    if need <= 0:
+        return None
+    ws = _attn_ws.get(device)
+    if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise IHError("attention workspace must be created before CUDA-graph capture (run one warm-up step)")
+        ws = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=device)
+        _attn_ws[device] = ws
+    return ws
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Nq: int, Nk: int, *,
-              n_ip: int = 0, ip_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B*Nq, >=H*64] / k, v [B*Nk, >=H*64] 2-D views (row stride arbitrary); returns [B*Nq, H*64]."""
+              n_ip: int = 0, ip_scale: float = 1.0, out: Optional[torch.Tensor] = None,
+              kv_split: bool = True) -> torch.Tensor:
+    """q [B*Nq, >=H*64] / k, v [B*Nk, >=H*64] 2-D views (row stride arbitrary); returns [B*Nq, H*64].
+    kv_split=False withholds the workspace, i.e. every query tile is processed whole (ih_attention_f16 behaviour)."""
     lib = _lib.load()
     _req(q, "q"); _req(k, "k"); _req(v, "v")
     if out is None:
         out = torch.empty((B * Nq, H * 64), dtype=torch.float16, device=q.device)
-    rc = lib.ih_attention_f16(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
-                              out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, n_ip, float(ip_scale), _stream())
-    check(rc, "ih_attention_f16")
+    ws = _attn_workspace(q.device, int(lib.ih_attention_workspace_bytes(B, H, Nq, Nk, n_ip))) if kv_split else None
+    rc = lib.ih_attention_ws_f16(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(),
+                                 _rows(v, "v"), out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, n_ip,
+                                 float(ip_scale), _p(ws), 0 if ws is None else ws.numel(), _stream())
+    check(rc, "ih_attention_ws_f16")
     return out
 
 

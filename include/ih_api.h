@@ -74,6 +74,15 @@ int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk,
                      void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
                      void* stream);
 
+/* ih_attention_f16 with a caller-owned scratch buffer (>= ih_attention_workspace_bytes(...) bytes, contents
+ * irrelevant).  With it the long self-attention shapes (Nk > 96, n_ip == 0) cut the query tiles that would otherwise
+ * form a nearly empty last wave into KV parts that share one wave and are merged by a second small kernel
+ * (flash-decoding style, fixed merge order: deterministic).  workspace == NULL behaves like ih_attention_f16. */
+long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip);
+int ih_attention_ws_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                        void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
+                        void* workspace, long long workspace_bytes, void* stream);
+
 /* GroupNorm over NHWC [B, HW, C] (optionally the channel-concatenation of two tensors x0 [.., C0] and x1 [.., C1]),
  * fp32 partial sums reduced in double, optional fused SiLU.  stats_ws: ih_groupnorm_workspace_bytes(B, groups) bytes,
  * zero-initialised ONCE by the caller (the kernels leave its ticket counters at zero again) and not shared by

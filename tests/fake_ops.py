@@ -104,7 +104,7 @@ def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, ou
     return y.to(x.dtype).contiguous()
 
 
-def attention(q, k, v, B, H, Nq, Nk, *, n_ip=0, ip_scale=1.0, out=None):
+def attention(q, k, v, B, H, Nq, Nk, *, n_ip=0, ip_scale=1.0, out=None, kv_split=True):
     _count[0] += 1
     C = H * 64
     qf = q.float().reshape(B, Nq, H, 64).transpose(1, 2)
