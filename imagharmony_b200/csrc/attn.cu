@@ -867,6 +867,8 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p) {
 // KV-split plan of the ping-pong kernel: with P query pairs on G SMs (one CTA per SM), the last P mod G pairs would
 // run as a nearly empty extra wave; they are cut into `split` KV parts each so that (P mod G) * split <= G CTAs share
 // that wave.  Returns split (1 = none) and the number of pairs processed whole.
+static int g_split_policy = 0;   // 0: cost model, 1: split whenever a split plan exists (tests)
+
 static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
   const int G = num_sms();
   const int rem = pairs % G;
@@ -879,7 +881,7 @@ static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
   // measured (tools/attn_probe.py): a KV iteration takes ~2.7 us with every SM busy but ~2.0 us in a sparsely filled
   // last wave; a part pays ~11 us on top of its iterations (CTA set-up, partial epilogue, merge kernel)
   const float t_whole = 2.0f * nb, t_split = 2.7f * ((nb + s - 1) / s) + 11.0f;
-  if (t_split >= t_whole) return;
+  if (t_split >= t_whole && g_split_policy == 0) return;
   *n_whole = pairs - rem;
   *split = s;
 }
@@ -887,6 +889,8 @@ static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
 }  // namespace ih
 
 using namespace ih;
+
+extern "C" void ih_attention_set_split_policy(int policy) { g_split_policy = policy; }
 
 extern "C" long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 96 || n_ip != 0) return 0;

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib
@@ -166,6 +168,44 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int,
                                  _rows(v, "v"), out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, n_ip,
                                  float(ip_scale), _p(ws), 0 if ws is None else ws.numel(), _stream())
     check(rc, "ih_attention_ws_f16")
+    return out
+
+
+# Measured on B200 (tools/attn_probe.py cross, profiles/): at UNet batch 2 the fused q-projection + cross-attention
+# kernel takes 32.4 us per layer against 26.8 us for projection GEMM + attention kernel -- its per-head attention
+# epilogue is a serial latency chain with nothing to overlap (one tile per CTA, TMEM full), while the stand-alone
+# kernel hides the same chain behind three co-resident CTAs per SM.  The processors therefore use it only on request.
+USE_FUSED_XATTN = os.environ.get("IH_XATTN_FUSED", "0") == "1"
+
+
+def xattn_q_fused_ok(Nq: int, Nk: int) -> bool:
+    """Shapes the fused q-projection + short-key cross-attention kernel covers (else: linear + attention)."""
+    return Nq % 128 == 0 and 0 < Nk <= 96
+
+
+def xattn_q_fused(h: torch.Tensor, wq: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Nq: int,
+                  Nk: int, *, n_ip: int = 0, ip_scale: float = 1.0, bias: Optional[torch.Tensor] = None, ln=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """attention(linear(h, wq, bias, ln=ln), k, v, ...) in one kernel: h [B*Nq, K] raw rows, wq [H*64, K],
+    k / v [B*Nk, >=H*64] views; `ln=(stats, eps)` as in linear().  Returns [B*Nq, H*64]."""
+    lib = _lib.load()
+    _req(h, "h"); _req(wq, "wq"); _req(k, "k"); _req(v, "v")
+    M, K = h.shape
+    if M != B * Nq or tuple(wq.shape) != (H * 64, K) or not wq.is_contiguous():
+        raise IHError(f"xattn_q_fused: h must be [{B * Nq}, K] and wq contiguous [{H * 64}, K]")
+    ln_stats, ln_slabs, ln_eps = None, 0, 0.0
+    if ln is not None:
+        ln_stats, ln_eps = ln
+        _req(ln_stats, "ln_stats", torch.float32)
+        if ln_stats.dim() != 3 or ln_stats.shape[1] != M or ln_stats.shape[0] != (K + 63) // 64 or not ln_stats.is_contiguous():
+            raise IHError("xattn_q_fused: ln statistics must be contiguous [ceil(K/64), M, 2]")
+        ln_slabs = ln_stats.shape[0]
+    if out is None:
+        out = torch.empty((M, H * 64), dtype=torch.float16, device=h.device)
+    rc = lib.ih_xattn_q_fused_f16(h.data_ptr(), _rows(h, "h"), wq.data_ptr(), _p(bias), _p(ln_stats), ln_slabs,
+                                  float(ln_eps), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                                  out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, n_ip, float(ip_scale), K, _stream())
+    check(rc, "ih_xattn_q_fused_f16")
     return out
 
 

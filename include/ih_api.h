@@ -79,6 +79,19 @@ int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk,
  * form a nearly empty last wave into KV parts that share one wave and are merged by a second small kernel
  * (flash-decoding style, fixed merge order: deterministic).  workspace == NULL behaves like ih_attention_f16. */
 long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip);
+/* Fused front half of a cross-attention layer: out = CrossAttn(LayerNorm(h) Wq^T, k, v) for short key axes (Nk <= 96,
+ * Nq % 128 == 0): the q projection (K input channels -> H*64) runs as a tcgen05 GEMM whose epilogue performs the
+ * (decoupled) attention per head, so q never goes to HBM.  h: [B*Nq, K] raw rows; wq: [H*64, K]; bias: [H*64] or NULL;
+ * ln_stats/ln_slabs/ln_eps as in ih_gemm_ln_f16 (NULL: no folded LayerNorm); k, v, n_ip, ip_scale, out as in
+ * ih_attention_f16.  Replaces attention_processor.py:396 (to_q) + :423-425, :440-442, :450 (IPAttnProcessor2_0) and
+ * :292, :312-314 (AttnProcessor2_0 with encoder_hidden_states). */
+int ih_xattn_q_fused_f16(const void* h, long long ldh, const void* wq, const void* bias, const void* ln_stats,
+                         int ln_slabs, float ln_eps, const void* k, long long ldk, const void* v, long long ldv,
+                         void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale, int K,
+                         void* stream);
+
+/* Test aid: 0 (default) = split only when the cost model predicts a gain, 1 = split whenever a plan exists. */
+void ih_attention_set_split_policy(int policy);
 int ih_attention_ws_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                         void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
                         void* workspace, long long workspace_bytes, void* stream);

@@ -37,6 +37,20 @@ def _check_sdxl_case(attn, hidden_states, attention_mask):
                       "connection, rescale_output_factor == 1)")
 
 
+def _cross_attention(attn, x, kv, B, N, Nk, C, *, n_ip=0, ip_scale=1.0, ln_stats=None, ln_eps=1e-5, need_q=False):
+    """to_q + (decoupled) SDPA over the cached [K | V] rows: projection GEMM + attention kernel, or (IH_XATTN_FUSED=1,
+    slower at UNet batch 2 -- see ops.USE_FUSED_XATTN) one fused kernel.  Returns (q or None, output [B*N, C])."""
+    if ln_stats is not None:
+        (w, bias), ln = attn._ln, (ln_stats, ln_eps)              # norm2 folded into to_q
+    else:
+        w, bias, ln = attn.to_q.weight, None, None
+    if ops.USE_FUSED_XATTN and not need_q and ops.xattn_q_fused_ok(N, Nk):
+        return None, ops.xattn_q_fused(x, w, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip, ip_scale=ip_scale,
+                                       bias=bias, ln=ln)
+    q = ops.linear(x, w, bias, ln=ln)
+    return q, ops.attention(q, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip, ip_scale=ip_scale)
+
+
 class AttnProcessor2_0(torch.nn.Module):
     """Self-attention (and plain cross-attention) processor -- reference AttnProcessor2_0 (:244-332).
 
@@ -67,13 +81,8 @@ class AttnProcessor2_0(torch.nn.Module):
             o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N)
         else:
             Nk = encoder_hidden_states.shape[1]
-            if ln_stats is not None:
-                w_c, c = attn._ln
-                q = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))
-            else:
-                q = ops.linear(x, attn.to_q.weight)
             kv = ops.linear(encoder_hidden_states.reshape(B * Nk, -1), attn.fused_kv_weight())
-            o = ops.attention(q, kv[:, :C], kv[:, C:], B, H, N, Nk)
+            _, o = _cross_attention(attn, x, kv, B, N, Nk, C, ln_stats=ln_stats, ln_eps=ln_eps)
         res2d = None if residual is None else residual.reshape(B * N, C)
         out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d,
                          stats_out=stats_out)                                     # :320 (+ fused h + ...)
@@ -158,14 +167,10 @@ class IPAttnProcessor2_0(torch.nn.Module):
             cached = self.prepare(attn, encoder_hidden_states)
         _, kv, Nk, n_ip = cached
         x = hidden_states.reshape(B * N, C)
-        if ln_stats is not None:
-            w_c, c = attn._ln
-            q = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))                      # norm2 folded into to_q (:396)
-        else:
-            q = ops.linear(x, attn.to_q.weight)                                   # :396
-        o = ops.attention(q, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip,
-                          ip_scale=float(self.scale))                             # :423-450
-        if self.keep_attn_map and not self.skip:
+        want_map = self.keep_attn_map and not self.skip
+        q, o = _cross_attention(attn, x, kv, B, N, Nk, C, n_ip=n_ip, ip_scale=float(self.scale), ln_stats=ln_stats,
+                                ln_eps=ln_eps, need_q=want_map)                   # :396, :423-450
+        if want_map:
             k_ip = kv.view(B, Nk, 2 * C)[:, Nk - n_ip:, :C].reshape(B, n_ip, attn.heads, 64).permute(0, 2, 1, 3)
             qh = q.reshape(B, N, attn.heads, 64).permute(0, 2, 1, 3)
             self.attn_map = qh @ k_ip.transpose(-2, -1).softmax(dim=-1)           # :443-444 (diagnostic only)

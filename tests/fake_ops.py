@@ -117,6 +117,18 @@ def attention(q, k, v, B, H, Nq, Nk, *, n_ip=0, ip_scale=1.0, out=None, kv_split
     return o.transpose(1, 2).reshape(B * Nq, C).to(q.dtype)
 
 
+USE_FUSED_XATTN = False
+
+
+def xattn_q_fused_ok(Nq, Nk):
+    return Nq % 128 == 0 and 0 < Nk <= 96
+
+
+def xattn_q_fused(h, wq, k, v, B, H, Nq, Nk, *, n_ip=0, ip_scale=1.0, bias=None, ln=None, out=None):
+    q = linear(h, wq, bias, ln=ln)
+    return attention(q, k, v, B, H, Nq, Nk, n_ip=n_ip, ip_scale=ip_scale)
+
+
 def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, out=None, ws=None):
     _count[0] += 2
     x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)

@@ -15,6 +15,7 @@ GROUPS = [
     ("tests/test_kernels_gpu.py", "test_gemm_geglu"),
     ("tests/test_kernels_gpu.py", "test_gemm_layernorm_fold"),
     ("tests/test_kernels_gpu.py", "test_attention_kv_split"),
+    ("tests/test_kernels_gpu.py", "test_xattn_q_fused"),
     ("tests/test_kernels_gpu.py", "test_conv3x3"),
     ("tests/test_kernels_gpu.py", "test_attention"),
     ("tests/test_kernels_gpu.py", "norm"),
