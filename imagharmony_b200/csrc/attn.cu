@@ -38,6 +38,7 @@ struct AttnParams {
   int H, qpairs, n_whole, split;
   float* ws_o;   // [slots][256][64]
   float* ws_ml;  // [slots][256][2]
+  long long* trace;  // optional clock64 stamps of CTA 0, KV blocks 4..7 (ih_attention_set_trace); nullptr in production
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -502,10 +503,33 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
 // O stays in TMEM across KV blocks (accumulating MMA); the running max is only raised when it grew by more than 2^8
 // ("lazy rescale"), in which case the row thread rescales its O row in TMEM (tcgen05.ld / tcgen05.st).
 // ================================================================================================================
-constexpr int A2_THREADS = 320;
+#ifndef IH_A2_POLY
+#define IH_A2_POLY 1
+#endif
+// which of every 8 exponentials are evaluated on the FMA pipe instead of MUFU (IH_A2_POLY of 8)
+#if IH_A2_POLY == 0
+#define A2_POLY(e) (false)
+#elif IH_A2_POLY == 1
+#define A2_POLY(e) ((e) == 3)
+#elif IH_A2_POLY == 2
+#define A2_POLY(e) ((e) == 2 || (e) == 6)
+#else
+#define A2_POLY(e) ((e) == 2 || (e) == 5 || (e) == 7)
+#endif
+// Optional clock64 trace of CTA 0 (KV blocks 4..7), compiled in with -DIH_ATTN_TRACE=1 (tools/attn_trace.py).
+#ifndef IH_ATTN_TRACE
+#define IH_ATTN_TRACE 0
+#endif
+#if IH_ATTN_TRACE
+#define A2_STAMP(cond, slot) do { if (cond) p.trace[slot] = clock64(); } while (0)
+#else
+#define A2_STAMP(cond, slot) do { } while (0)
+#endif
+constexpr int A2_THREADS = 576;  // warp 0 TMA, warp 1 MMA, 8 softmax warps per query tile (two threads per row)
 constexpr int A2_KS = 3;  // K / V stages
 constexpr int A2_SMEM_TILES = ATT_TILE * (2 + 2 * A2_KS) + 4 * ATT_TILE;  // Q_A Q_B | K[KS] | V[KS] | P_A P_B
-constexpr int A2_SMEM_BYTES = A2_SMEM_TILES + 256;
+constexpr int A2_XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // [parity][tile][half][row] fp32: row max / row sum exchange
+constexpr int A2_SMEM_BYTES = A2_SMEM_TILES + 256 + A2_XCH_BYTES;
 
 __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
@@ -526,7 +550,10 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
   uint64_t* s_full = v_empty + A2_KS;       // [2]
   uint64_t* p_full = s_full + 2;            // [2]
   uint64_t* o_full = p_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;            // [2] all row threads hold their scores of the block in registers
+  uint64_t* pv_done = s_free + 2;           // [2] PV MMA of the block has completed: P may be rewritten, O rescaled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(smem + A2_SMEM_TILES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -551,7 +578,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 256);
+      mbar_init(&s_free[t], 256);
+      mbar_init(&pv_done[t], 1);
       mbar_init(&o_full[t], 1);
     }
     for (int s = 0; s < A2_KS; ++s) {
@@ -594,217 +623,240 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the issue loop (uniform control flow); one elected lane issues the MMAs and commits.
+    {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
       const int ntiles = tileB_active ? 2 : 1;
-      uint64_t q_desc[2];
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&q_full[t], 0);
-        q_desc[t] = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE));
-      }
+      for (int t = 0; t < ntiles; ++t) mbar_wait(&q_full[t], 0);
+      const uint32_t q_lo = smem_u32(sQ), k_lo = smem_u32(sK), v_lo = smem_u32(sV);
       auto issue_s = [&](int t, int stage) {
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + stage * ATT_TILE));
+        const uint64_t q_desc = umma_desc_sw128(q_lo + t * ATT_TILE);
+        const uint64_t k_desc = umma_desc_sw128(k_lo + stage * ATT_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_base + t * 128, q_desc[t] + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[t]);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int stage, bool accumulate) {
-        const uint32_t v_addr = smem_u32(sV + stage * ATT_TILE);
-        const uint32_t p_addr = smem_u32(sP + t * 2 * ATT_TILE);
+        // P(t) lives in TENSOR memory: fp16 pairs in columns [384 + 64 t, +64) (8 columns per 16-key step), written
+        // by the softmax threads with tcgen05.st -- the A operand costs no shared-memory bandwidth.
+        // V: +128 descriptor units (2 KiB) per 16 keys of the MN-major tile.
+        const uint64_t v_desc = umma_desc_sw128(v_lo + stage * ATT_TILE);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t p_desc = umma_desc_sw128(p_addr + (kk >> 2) * ATT_TILE) + 2 * (kk & 3);
-          const uint64_t v_desc = umma_desc_sw128(v_addr + kk * 2048);
-          umma_f16_ss(tmem_base + 256 + t * 64, p_desc, v_desc, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + 8 * kk, v_desc + kk * (2048 >> 4), idesc_o,
+                        (accumulate || kk != 0) ? 1u : 0u);
         }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       // prologue: S(0) for both tiles
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
-      umma_commit(&k_empty[0]);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nb; ++j) {
-        int s1 = s + 1;
-        uint32_t ph1 = ph;
-        if (s1 == A2_KS) {
-          s1 = 0;
-          ph1 ^= 1;
-        }
-        const bool more = (j + 1 < nb);
+      commit(&k_empty[0]);
+      // Event loop.  The row threads keep their scores in registers, so S(t, j+1) = Q K_{j+1}^T may overwrite the S
+      // columns as soon as every thread has LOADED block j (s_free) -- the next scores are ready long before the
+      // softmax of block j ends; PV(t, j) follows p_full(t, j) and reads P from its own TMEM columns.  Nothing here
+      // blocks: an event is taken only when its operand tile has landed too, so a tile that runs ahead can never
+      // starve the other tile's MMAs (and with them the producer's stage recycling).
+      auto ready = [&](uint64_t* bar, uint32_t parity) { return __any_sync(0xffffffffu, mbar_test_wait(bar, parity)) != 0; };
+      int js[2] = {1, 1};   // next S block to issue
+      int jp[2] = {0, 0};   // next PV block to issue
+      if (ntiles == 1) js[1] = jp[1] = nb;
+      uint32_t idle = 0;
+      while (jp[0] < nb || jp[1] < nb) {
+        bool progressed = false;
         for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          if (t == 0) mbar_wait(&v_full[s], ph);
-          tc_fence_after();
-          issue_pv(t, s, j != 0);
-          if (t == ntiles - 1) umma_commit(&v_empty[s]);
-          if (more) {
-            if (t == 0) {
-              mbar_wait(&k_full[s1], ph1);
-              tc_fence_after();
-            }
-            issue_s(t, s1);
-            if (t == ntiles - 1) umma_commit(&k_empty[s1]);
-          } else {
-            umma_commit(&o_full[t]);
+          if (js[t] < nb && ready(&s_free[t], (js[t] - 1) & 1) && ready(&k_full[js[t] % A2_KS], (js[t] / A2_KS) & 1)) {
+            const int j = js[t], s = j % A2_KS;
+            tc_fence_after();
+            issue_s(t, s);
+            ++js[t];
+            if (js[t ^ 1] > j) commit(&k_empty[s]);     // the other tile's S of block j was issued earlier
+            progressed = true;
+          }
+          if (jp[t] < nb && ready(&p_full[t], jp[t] & 1) && ready(&v_full[jp[t] % A2_KS], (jp[t] / A2_KS) & 1)) {
+            const int j = jp[t], s = j % A2_KS;
+            tc_fence_after();
+            issue_pv(t, s, j != 0);
+            commit(&pv_done[t]);
+            if (j == nb - 1) commit(&o_full[t]);
+            ++jp[t];
+            if (jp[t ^ 1] > j) commit(&v_empty[s]);
+            progressed = true;
           }
         }
-        s = s1;
-        ph = ph1;
+        if (progressed) idle = 0;
+        else if (++idle > IH_SPIN_LIMIT) __trap();
       }
     }
-    __syncwarp();
   } else {
-    const int t = (warp - 2) >> 2;  // tile
+    // Two threads per query row: thread (r, hh) owns columns [64 hh, 64 hh + 64) of each 128-key S block, half of the O
+    // row, and half of the exponentials.  Four softmax warps per SM sub-partition (instead of two) hide the dependent-
+    // issue latency of the exp / max / sum chains, which is what bounded the one-thread-per-row version (ncu: 0.44
+    // IPC, 5 cycles between a warp's issues).  The partners (warps w and w + 4: same TMEM lane quarter) meet once per
+    // block on a 64-thread named barrier to exchange their half-row maxima.
+    const int idx = warp - 2;
+    const int t = idx >> 3;            // tile
+    const int hh = (idx >> 2) & 1;     // column half
     if (t == 0 || tileB_active) {
       const int q = warp & 3;
       const int r = q * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-      const uint32_t tS = tmem_base + t * 128 + lane_base;
-      const uint32_t tO = tmem_base + 256 + t * 64 + lane_base;
-      uint8_t* p_row = sP + t * 2 * ATT_TILE + r * 128;
-      const int rx = r & 7;
+      const uint32_t tS = tmem_base + t * 128 + hh * 64 + lane_base;
+      const uint32_t tO = tmem_base + 256 + t * 64 + hh * 32 + lane_base;
+      const uint32_t tP = tmem_base + 384 + t * 64 + hh * 32 + lane_base;   // fp16 pairs of my 64 keys
       const float sl2 = p.scale_log2;
+      const uint32_t pair_bar = 1 + t * 4 + q;          // named barrier of the two partner warps
+      float* x_mine = xch + (t * 2 + hh) * 128 + r;     // + parity * 512
+      float* x_peer = xch + (t * 2 + (hh ^ 1)) * 128 + r;
       float m_used = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < nb; ++j) {
+#if IH_ATTN_TRACE
+        const bool trj = p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && hh == 0 && j >= 4 && j < 8;
+        const int tb = t * 64 + (j - 4) * 8;
+#endif
+        A2_STAMP(trj, tb + 0);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        const int valid = p.Nk - (jb + j) * 128;
-        // pass 1: row max (two 32-column TMEM loads in flight per wait)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        A2_STAMP(trj, tb + 1);
+        const int valid = p.Nk - (jb + j) * 128 - hh * 64;   // valid keys among my 64 columns
+        // My 64 scores are read from TMEM exactly ONCE and stay in registers for both the max and the exp pass: TMEM
+        // reads run at 64 B/clk/SM, so a second sweep over the 128 x 128 fp32 S tiles of both query tiles would cost
+        // more (2 x 2048 cycles per KV block) than all the arithmetic.
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(tS, va);
+        tmem_ld_32x32b_x32(tS + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);   // the S columns may be overwritten with the next block's scores
+        A2_STAMP(trj, tb + 2);
+        if (valid < 64) {
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32b_x32(tS + hlf * 64, va);
-          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
-          tmem_ld_wait();
-          if (valid < 128) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;  // -inf
-              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            mx0 = fmax3(mx0, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(vb[e]), __uint_as_float(vb[e + 1]));
+          for (int e = 0; e < 32; ++e) {
+            if (e >= valid) va[e] = 0xff800000u;  // -inf
+            if (32 + e >= valid) vb[e] = 0xff800000u;
           }
         }
-        const float m_blk = fmaxf(mx0, mx1) * sl2;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          mx0 = fmax3(mx0, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(vb[e]), __uint_as_float(vb[e + 1]));
+        }
+        const float mx_mine = fmaxf(mx0, mx1);
+        x_mine[(j & 1) * 512] = mx_mine;
+        A2_STAMP(trj, tb + 3);
+        named_bar_sync(pair_bar, 64);
+        A2_STAMP(trj, tb + 4);
+        const float m_blk = fmaxf(mx_mine, x_peer[(j & 1) * 512]) * sl2;
         if (j == 0) {
           m_used = m_blk;
         } else {
-          const bool need = m_blk > m_used + 8.0f;
+          const bool need = m_blk > m_used + 8.0f;      // same decision in both partners (same m_blk, same m_used)
           if (__any_sync(0xffffffffu, need)) {
             const float m_new = need ? m_blk : m_used;
             const float alpha = ex2_approx(m_used - m_new);
             m_used = m_new;
             l_run *= alpha;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t ov[32];
-              tmem_ld_32x32b_x32(tO + c * 32, ov);
+            mbar_wait(&pv_done[t], (j - 1) & 1);        // O must hold every block up to j - 1 before it is rescaled
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {               // my half (32 columns) of the O row, 16 at a time
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(tO + c * 16, ov);
               tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-              tmem_st_32x32b_x32(tO + c * 32, ov);
+              for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+              tmem_st_32x32b_x16(tO + c * 16, ov);
             }
             tmem_st_wait();
           }
         }
-        // pass 2: p = 2^(s*scale - m) -> fp16 P tile (A operand of the PV MMA), row sum
+        // p = 2^(s*scale - m) -> fp16 pairs, stored to the tile's P columns in TMEM (the A operand of the PV MMA): my 64
+        // keys = columns [32 hh, 32 hh + 32) of the 64.
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32b_x32(tS + hlf * 64, va);
-          tmem_ld_32x32b_x32(tS + hlf * 64 + 32, vb);
-          tmem_ld_wait();
-          if (valid < 128) {
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (hlf * 64 + e >= valid) va[e] = 0xff800000u;
-              if (hlf * 64 + 32 + e >= valid) vb[e] = 0xff800000u;
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t* src = (g < 4) ? (va + g * 8) : (vb + (g - 4) * 8);
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t* src = (hf == 0 ? va : vb) + g * 8;
             float pr[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float xarg = fmaf(__uint_as_float(src[e]), sl2, -m_used);
-              // 3 of every 8 exponentials on the FMA pipe, 5 on the MUFU pipe (balances the two pipes)
-              pr[e] = (e == 2 || e == 5 || e == 7) ? ex2_poly(xarg) : ex2_approx(xarg);
+              // a share of the exponentials runs on the FMA pipe instead of MUFU (IH_A2_POLY of every 8)
+              pr[e] = A2_POLY(e) ? ex2_poly(xarg) : ex2_approx(xarg);
             }
             sum0 += (pr[0] + pr[1]) + (pr[2] + pr[3]);
             sum1 += (pr[4] + pr[5]) + (pr[6] + pr[7]);
-            uint4 o;
-            o.x = pack_half2(pr[0], pr[1]);
-            o.y = pack_half2(pr[2], pr[3]);
-            o.z = pack_half2(pr[4], pr[5]);
-            o.w = pack_half2(pr[6], pr[7]);
-            // 16-byte chunk g of key half `hlf`, XOR-swizzled with the row (SWIZZLE_128B)
-            *reinterpret_cast<uint4*>(p_row + hlf * ATT_TILE + ((g ^ rx) << 4)) = o;
+            pk[g * 4 + 0] = pack_half2(pr[0], pr[1]);
+            pk[g * 4 + 1] = pack_half2(pr[2], pr[3]);
+            pk[g * 4 + 2] = pack_half2(pr[4], pr[5]);
+            pk[g * 4 + 3] = pack_half2(pr[6], pr[7]);
           }
+          // PV(t, j - 1) must have consumed the previous P before it is overwritten; half a block of exponentials after
+          // it was issued it normally has.  (This also keeps p_full at most one phase ahead of the MMA warp.)
+          if (hf == 0 && j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);
+          tmem_st_32x32b_x16(tP + hf * 16, pk);
         }
+        tmem_st_wait();
         l_run += sum0 + sum1;
+        A2_STAMP(trj, tb + 5);
         tc_fence_before();
-        fence_proxy_async_smem();
         mbar_arrive(&p_full[t]);
+        A2_STAMP(trj, tb + 6);
       }
 
-      // epilogue: O / l -> global, or the un-normalised partial (O, m, l) -> workspace for a KV part
+      // epilogue: the partners add their half-row sums; each writes its 32 of the 64 output columns
+      x_mine[(nb & 1) * 512] = l_run;
+      named_bar_sync(pair_bar, 64);
+      const float l_tot = l_run + x_peer[(nb & 1) * 512];
       mbar_wait(&o_full[t], 0);
       tc_fence_after();
       const int qrow = q0 + t * 128 + r;
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(tO, ov);
+      tmem_ld_wait();
       if (slot >= 0) {
         // the fp32 O tile goes through this tile's (now idle) P buffer and leaves as ONE 32 KiB bulk copy; 16-byte chunk
         // c of row r sits at chunk position c ^ (r & 15) (bank-conflict-free staging; attn_combine_kernel undoes it)
         const long long wrow = (long long)slot * 256 + t * 128 + r;
         uint8_t* stage = sP + t * 2 * ATT_TILE;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t ov[32];
-          tmem_ld_32x32b_x32(tO + c * 32, ov);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(stage + r * 256 + (((c * 8 + g) ^ (r & 15)) << 4)) =
-                make_uint4(ov[g * 4 + 0], ov[g * 4 + 1], ov[g * 4 + 2], ov[g * 4 + 3]);
-        }
-        reinterpret_cast<float2*>(p.ws_ml)[wrow] = make_float2(m_used, l_run);
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stage + r * 256 + (((hh * 8 + g) ^ (r & 15)) << 4)) =
+              make_uint4(ov[g * 4 + 0], ov[g * 4 + 1], ov[g * 4 + 2], ov[g * 4 + 3]);
+        if (hh == 0) reinterpret_cast<float2*>(p.ws_ml)[wrow] = make_float2(m_used, l_tot);
         fence_proxy_async_smem();
-        named_bar_sync(1 + t, 128);
-        if (q == 0 && lane == 0) {
+        named_bar_sync(9 + t, 256);
+        if (hh == 0 && q == 0 && lane == 0) {
           bulk_store_linear(p.ws_o + ((long long)slot * 256 + t * 128) * 64, stage, 2 * ATT_TILE);
           tma_store_commit();
           tma_store_wait_all();
         }
-      } else {
-        const float inv = 1.f / l_run;
-        __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
+      } else if (qrow < p.Nq) {
+        const float inv = 1.f / l_tot;
+        __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64 + hh * 32;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t ov[32];
-          tmem_ld_32x32b_x32(tO + c * 32, ov);
-          tmem_ld_wait();
-          if (qrow < p.Nq) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
-              o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
-              o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
-              o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
-            }
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+          o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+          o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+          o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + g * 8) = o;
         }
       }
     }
@@ -867,6 +919,7 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p) {
 // KV-split plan of the ping-pong kernel: with P query pairs on G SMs (one CTA per SM), the last P mod G pairs would
 // run as a nearly empty extra wave; they are cut into `split` KV parts each so that (P mod G) * split <= G CTAs share
 // that wave.  Returns split (1 = none) and the number of pairs processed whole.
+static long long* g_attn_trace = nullptr;
 static int g_split_policy = 0;   // 0: cost model, 1: split whenever a split plan exists (tests)
 
 static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
@@ -891,6 +944,7 @@ static void attn2_plan(int pairs, int nb, int* n_whole, int* split) {
 using namespace ih;
 
 extern "C" void ih_attention_set_split_policy(int policy) { g_split_policy = policy; }
+extern "C" void ih_attention_set_trace(void* device_buffer) { g_attn_trace = (long long*)device_buffer; }
 
 extern "C" long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 96 || n_ip != 0) return 0;
@@ -945,6 +999,7 @@ extern "C" int ih_attention_ws_f16(const void* q, long long ldq, const void* k, 
   p.ip_scale = ip_scale;
   p.out = (__half*)out;
   p.ldo = ldo;
+  p.trace = g_attn_trace;
 
   static bool configured = false;
   if (!configured) {

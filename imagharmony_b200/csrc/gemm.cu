@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // (whole warp, uniform control flow; one elected lane arms the barrier and issues the loads)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -176,7 +177,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          if (PAIR) {
+          if (!elect_one()) {
+            // not the issuing lane
+          } else if (PAIR) {
             // both CTAs' bytes complete on the leader's barrier; only the leader arms it
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
             if (p.mode == 0) {
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               tma_load_2d(sB, &bmap, &full_bar[stage], kb * BK, n0);
             }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -216,8 +220,11 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+    // lane issues the MMAs and commits -- see elect_one() in ptx.cuh.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN, false, false);
+      const uint32_t smem_lo = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -229,26 +236,32 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (it == 0 && kb == 0) stamp(3);
+          if (lane == 0 && it == 0 && kb == 0) stamp(3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t a_addr = smem_lo + stage * S::STAGE_BYTES;
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-            if (PAIR) umma_f16_ss_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 bytes per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+              if (PAIR) umma_f16_ss_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (PAIR) umma_commit_2sm(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
           }
-          if (PAIR) umma_commit_2sm(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (PAIR) umma_commit_2sm(&tmem_full_bar[acc]);
-        else umma_commit(&tmem_full_bar[acc]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_2sm(&tmem_full_bar[acc]);
+          else umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();

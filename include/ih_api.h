@@ -92,6 +92,10 @@ int ih_xattn_q_fused_f16(const void* h, long long ldh, const void* wq, const voi
 
 /* Test aid: 0 (default) = split only when the cost model predicts a gain, 1 = split whenever a plan exists. */
 void ih_attention_set_split_policy(int policy);
+/* Debug aid (effective only in builds with -DIH_ATTN_TRACE=1): CTA 0 of later ping-pong attention launches writes
+ * clock64 stamps of KV blocks 4..7 into this device buffer (>= 192 int64: softmax thread of tile 0 at [0,64), of tile
+ * 1 at [64,128)); NULL disables.  See tools/attn_trace.py and profiles/r1_attn_trace.md. */
+void ih_attention_set_trace(void* device_buffer);
 int ih_attention_ws_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                         void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
                         void* workspace, long long workspace_bytes, void* stream);
