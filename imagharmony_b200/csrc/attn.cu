@@ -368,26 +368,29 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
       tma_load_3d(sV, &tmV, v_full, head * 64, 0, b);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
-      mbar_wait(qk_full, 0);
-      tc_fence_after();
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
+    // whole warp, uniform control flow; one elected lane issues (see elect_one() in ptx.cuh)
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);
+    mbar_wait(qk_full, 0);
+    tc_fence_after();
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t k_desc = umma_desc_sw128(smem_u32(sK));
+    if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
       umma_commit(s_full);
-      mbar_wait(p_full, 0);
-      mbar_wait(v_full, 0);
-      tc_fence_after();
-      const uint32_t v_addr = smem_u32(sV);
+    }
+    __syncwarp();
+    mbar_wait(v_full, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
+    const uint64_t v_desc = umma_desc_sw128(smem_u32(sV));
+    if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < 6; ++kk) {
-        const uint64_t p_desc = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * ATT_TILE) + 2 * (kk & 3);
-        const uint64_t v_desc = umma_desc_sw128(v_addr + kk * 2048);
-        umma_f16_ss(tmem_base, p_desc, v_desc, idesc_o, kk != 0);   // O overlays the (already consumed) S columns
-      }
+      for (int kk = 0; kk < 6; ++kk)   // O overlays the (already consumed) S columns
+        umma_f16_ss(tmem_base, p_desc + ((kk >> 2) * (ATT_TILE >> 4) + 2 * (kk & 3)), v_desc + kk * (2048 >> 4), idesc_o,
+                    kk != 0);
       umma_commit(o_full);
     }
     __syncwarp();

@@ -101,16 +101,19 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
   pdl_wait();
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (whole warp; one elected lane issues) ------------------------------
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sA = smem + stage * QX_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], QX_STAGE_BYTES);
-        tma_load_2d(sA, &tmA, &full_bar[stage], kb * QX_BK, m0);
-        tma_load_2d(sA + QX_A_BYTES, &tmW, &full_bar[stage], kb * QX_BK, head0 * 64);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], QX_STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full_bar[stage], kb * QX_BK, m0);
+          tma_load_2d(sA + QX_A_BYTES, &tmW, &full_bar[stage], kb * QX_BK, head0 * 64);
+        }
+        __syncwarp();
         if (++stage == QX_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -122,12 +125,15 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
         if (nh <= 0) break;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* base = smem + stage * QX_STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[pair], nh * 2 * QX_KV_TILE);
-        for (int i = 0; i < nh; ++i) {
-          const int head = head0 + 2 * pair + i;
-          tma_load_3d(base + (2 * i) * QX_KV_TILE, &tmK, &kv_full[pair], head * 64, 0, b);
-          tma_load_3d(base + (2 * i + 1) * QX_KV_TILE, &tmV, &kv_full[pair], head * 64, 0, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[pair], nh * 2 * QX_KV_TILE);
+          for (int i = 0; i < nh; ++i) {
+            const int head = head0 + 2 * pair + i;
+            tma_load_3d(base + (2 * i) * QX_KV_TILE, &tmK, &kv_full[pair], head * 64, 0, b);
+            tma_load_3d(base + (2 * i + 1) * QX_KV_TILE, &tmV, &kv_full[pair], head * 64, 0, b);
+          }
         }
+        __syncwarp();
         if (++stage == QX_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -135,27 +141,31 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (projection main loop) ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (projection main loop; whole warp, elected lane issues) ----------
+    {
       constexpr uint32_t idesc = umma_idesc_f16(QX_BM, QX_BN, false, false);
+      const uint32_t smem_lo = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * QX_STAGE_BYTES);
+        const uint32_t a_addr = smem_lo + stage * QX_STAGE_BYTES;
         const uint64_t a_desc = umma_desc_sw128(a_addr);
         const uint64_t b_desc = umma_desc_sw128(a_addr + QX_A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < QX_BK / 16; ++k)
-          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < QX_BK / 16; ++k)
+            umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
         if (++stage == QX_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
     }
     __syncwarp();
   } else {
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
     const int slot = (warp - 2) >> 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
-    const bool elected = (q == 0 && lane == 0);  // issues this slot's attention MMAs
+    const bool issuer = (q == 0);                // this warp issues the slot's attention MMAs (elected lane)
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tAcc = tmem_base + lane_base;
     const uint32_t tS_mma = tmem_base + 256 + slot * 128;
@@ -234,14 +244,17 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1 + slot, 128);
-      if (elected) {
+      if (issuer) {
         mbar_wait(&kv_full[hd >> 1], 0);
         tc_fence_after();
         const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
         const uint64_t k_desc = umma_desc_sw128(smem_u32(kv_base));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tS_mma, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[slot]);
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tS_mma, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[slot]);
+        }
+        __syncwarp();
       }
       mbar_wait(&s_full[slot], i & 1);
       tc_fence_after();
@@ -307,16 +320,18 @@ __global__ void __launch_bounds__(QX_THREADS, 1) qxattn_f16_kernel(const __grid_
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1 + slot, 128);
-      if (elected) {
+      if (issuer) {
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(kv_base + QX_KV_TILE);
+        const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
+        const uint64_t v_desc = umma_desc_sw128(smem_u32(kv_base + QX_KV_TILE));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 6; ++kk) {
-          const uint64_t p_desc = umma_desc_sw128(smem_u32(sP) + (kk >> 2) * QX_Q_TILE) + 2 * (kk & 3);
-          const uint64_t v_desc = umma_desc_sw128(v_addr + kk * 2048);
-          umma_f16_ss(tS_mma, p_desc, v_desc, idesc_o, kk != 0);   // O overlays the (already consumed) S columns
+          for (int kk = 0; kk < 6; ++kk)   // O overlays the (already consumed) S columns
+            umma_f16_ss(tS_mma, p_desc + ((kk >> 2) * (QX_Q_TILE >> 4) + 2 * (kk & 3)), v_desc + kk * (2048 >> 4),
+                        idesc_o, kk != 0);
+          umma_commit(&o_full[slot]);
         }
-        umma_commit(&o_full[slot]);
+        __syncwarp();
       }
       mbar_wait(&o_full[slot], i & 1);
       tc_fence_after();

@@ -5,9 +5,8 @@ PyTorch/CPU fallback: a CPU tensor or a missing library raises.
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import os
+from typing import Optional
 
 import torch
 
@@ -172,7 +171,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int,
 
 
 # Measured on B200 (tools/attn_probe.py cross, profiles/): at UNet batch 2 the fused q-projection + cross-attention
-# kernel takes 32.4 us per layer against 26.8 us for projection GEMM + attention kernel -- its per-head attention
+# kernel takes 28.6 us per layer against 25.2 us for projection GEMM + attention kernel -- its per-head attention
 # epilogue is a serial latency chain with nothing to overlap (one tile per CTA, TMEM full), while the stand-alone
 # kernel hides the same chain behind three co-resident CTAs per SM.  The processors therefore use it only on request.
 USE_FUSED_XATTN = os.environ.get("IH_XATTN_FUSED", "0") == "1"
