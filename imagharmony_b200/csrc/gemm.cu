@@ -554,10 +554,11 @@ static int pick_bn(long long m_tiles, int N) {
   const int sms = num_sms();
   double best = 1e30;
   int best_bn = 256;
-  // per-tile main-loop cost relative to the 128x256 tile (narrower tiles move more operand bytes per FLOP):
-  // measured 8192^3: 256 -> 1.0, 128 -> 0.75 (not 0.5); 192 interpolated
+  // per-tile main-loop cost relative to the 128x256 tile.  Measured per 64-deep k-block with 144 CTAs busy
+  // (tools/ab_probe.py tile): 0.350 us (256), 0.276 us (192), 0.257 us (128) -- the narrow tiles move more operand
+  // bytes per FLOP and the main loop is bound by the L2 -> SM operand stream (~19 TB/s aggregate), not by the MMA.
   const int cands[3] = {256, 192, 128};
-  const double tile_cost[3] = {2.0, 1.65, 1.5};
+  const double tile_cost[3] = {2.0, 1.58, 1.47};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
