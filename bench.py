@@ -232,31 +232,40 @@ def time_dominant_kernel(iters: int = 30):
 
 def run_pns(args, eng, cfg, lat, K, W, rank, world, device, dist):
     """PNS N candidates: shard seeds over ranks, K-step trajectories in batches, score, all_gather, argmax."""
-    from imagharmony_b200.pns import LinearProbeScorer, pns_select, shard_seeds
+    from imagharmony_b200.pns import LinearProbeScorer, pns_select, pns_two_phase, shard_seeds
     from imagharmony_b200.scheduler import EulerDiscreteScheduler
     N = args.pns
     seeds = [5000 + i for i in range(N)]
     ins = EulerDiscreteScheduler().set_timesteps(K).init_noise_sigma
     _, pos1, neg1, pooled1, npooled1, tid1 = synth_inputs(cfg, 1, lat, K, 0)
 
+    P = max(0, min(args.pns_preview, K))               # two-phase PNS: P preview steps for everyone, K - P for the winner
+    rep = lambda t, b: t.repeat(b, *([1] * (t.dim() - 1))).pin_memory()  # noqa: E731
+
     def run_candidates(batch_seeds):
         b = len(batch_seeds)
         lat0 = torch.cat([torch.randn((1, 4, lat, lat), generator=torch.Generator("cpu").manual_seed(s))
                           for s in batch_seeds]) * ins
-        rep = lambda t: t.repeat(b, *([1] * (t.dim() - 1))).pin_memory()  # noqa: E731
-        return eng.run(lat0.half().pin_memory(), rep(pos1), rep(neg1), rep(pooled1), rep(npooled1), rep(tid1), K,
-                       guidance_scale=5.0, ip_scale=1.0)
+        return eng.run(lat0.half().pin_memory(), rep(pos1, b), rep(neg1, b), rep(pooled1, b), rep(npooled1, b),
+                       rep(tid1, b), K, guidance_scale=5.0, ip_scale=1.0, stop_after=(P if P else None))
+
+    def run_rest(preview):
+        return eng.run(preview, rep(pos1, 1), rep(neg1, 1), rep(pooled1, 1), rep(npooled1, 1), rep(tid1, 1), K,
+                       guidance_scale=5.0, ip_scale=1.0, start_step=P)
 
     scorer = LinearProbeScorer(4 * lat * lat, seed=99, device=device)
     mine = shard_seeds(seeds, rank, world)
     if mine:                                           # warm-up: capture the graphs for this rank's batch sizes
-        for bsz in sorted({min(args.pns_batch, len(mine)), len(mine) % args.pns_batch or args.pns_batch}):
+        for bsz in sorted({min(args.pns_batch, len(mine)), len(mine) % args.pns_batch or args.pns_batch} | ({1} if P else set())):
             eng.run(*[t.pin_memory() for t in synth_inputs(cfg, bsz, lat, K, rank)], K, stop_after=W)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = pns_select(run_candidates, seeds, scorer, dist=dist, max_batch=args.pns_batch)
+    if P:
+        res = pns_two_phase(run_candidates, run_rest, seeds, scorer, dist=dist, max_batch=args.pns_batch)
+    else:
+        res = pns_select(run_candidates, seeds, scorer, dist=dist, max_batch=args.pns_batch)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if dist is not None:
@@ -264,14 +273,16 @@ def run_pns(args, eng, cfg, lat, K, W, rank, world, device, dist):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         wall = float(tt[0])
     if rank == 0:
-        line = {"metric": METRIC + " -- PNS", "value": N * K / wall, "unit": "denoise-steps/s", "n_gpus": world,
+        steps_done = N * (P if P else K) + (K - P if P else 0)     # trajectory steps actually executed for the result
+        line = {"metric": METRIC + " -- PNS", "value": steps_done / wall, "unit": "denoise-steps/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": f"PNS N={N} candidate noises, {args.res}x{args.res}, {K} steps each, "
+                "config": {"workload": f"PNS N={N} candidate noises, {args.res}x{args.res}, "
+                                       + (f"{P} preview steps each + {K - P} steps for the winner, " if P else f"{K} steps each, ") +
                                        f"{args.pns_batch} candidates per batch, score = fixed random linear probe of the "
                                        f"final latent, all_gather of N fp32 scores + broadcast of the winner",
                            "pns_edits_per_s": N / wall, "pns_wall_s": wall, "best_seed": res.best_seed},
-                "e2e": {"value": N * K / wall, "unit": "denoise-steps/s",
+                "e2e": {"value": steps_done / wall, "unit": "denoise-steps/s",
                         "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                         "note": "PNS wall clock includes H2D of every candidate batch and the score gather"},
                 "gpu_launches": int(eng.last_launches_per_step * K * ((len(mine) + args.pns_batch - 1) // args.pns_batch))}
@@ -290,6 +301,8 @@ def main():
     ap.add_argument("--pns", type=int, default=0,
                     help="PNS mode: N candidate noises in total, sharded over the ranks (BASELINE config 4: N=32 on 8 GPUs)")
     ap.add_argument("--pns-batch", type=int, default=4, help="candidates denoised together per rank (UNet batch 2x)")
+    ap.add_argument("--pns-preview", type=int, default=0,
+                    help="two-phase PNS: preview steps per candidate before the judge; the winner alone runs the rest")
     args = ap.parse_args()
 
     if args.impl == "reference":

@@ -70,9 +70,11 @@ class DenoiseEngine:
     def run(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, negative_prompt_embeds: torch.Tensor,
             pooled: torch.Tensor, negative_pooled: torch.Tensor, time_ids: torch.Tensor, num_inference_steps: int,
             guidance_scale: float = 5.0, ip_scale: float = 1.0, control_guidance_start: float = 0.0,
-            control_guidance_end: float = 1.0, stop_after: Optional[int] = None) -> torch.Tensor:
+            control_guidance_end: float = 1.0, stop_after: Optional[int] = None, start_step: int = 0) -> torch.Tensor:
         """latents [n,4,h,w] (already scaled by init_noise_sigma; host or device); embeds host or device tensors.
-        Returns the final latents as a new device tensor. `stop_after` runs only the first k steps (PNS preview)."""
+        Returns the latents after the last executed step as a new device tensor.  `stop_after` stops after step index
+        k - 1 (PNS preview); `start_step` = k resumes a trajectory whose `latents` are the output of a `stop_after=k`
+        call with the same schedule (two-phase PNS: preview all candidates, continue only the winner)."""
         if guidance_scale <= 1.0:
             raise IHError("the native loop implements the classifier-free-guidance path (guidance_scale > 1)")
         n, _, h, w = latents.shape
@@ -88,9 +90,11 @@ class DenoiseEngine:
         st["text_embeds"][n:].copy_(pooled, non_blocking=True)
         st["time_ids"][:n].copy_(time_ids, non_blocking=True)
         st["time_ids"][n:].copy_(time_ids, non_blocking=True)
-        st["step"].zero_()
+        if not 0 <= start_step <= T:
+            raise IHError(f"start_step {start_step} outside the {T}-step schedule")
+        st["step"].fill_(start_step)
         self.unet.prepare_conditioning(st["ehs"], st["text_embeds"], st["time_ids"])
-        ops.scale_model_input(st["latents"], st["model_in"], sigmas, st["step"])   # :332-334 for step 0
+        ops.scale_model_input(st["latents"], st["model_in"], sigmas, st["step"])   # :332-334 for the first step run
 
         steps = T if stop_after is None else min(stop_after, T)
 
@@ -102,16 +106,17 @@ class DenoiseEngine:
             return (n, h, w, L, T, float(guidance_scale), scale)
 
         if self.use_cuda_graph:
-            missing = sorted({scale_at(i) for i in range(steps)} - {k[-1] for k in self._graphs if k[:-1] == gkey(0.0)[:-1]})
+            missing = sorted({scale_at(i) for i in range(start_step, steps)} -
+                             {k[-1] for k in self._graphs if k[:-1] == gkey(0.0)[:-1]})
             if missing:
                 for sc in missing:
                     self.set_scale(sc)
                     self._graphs[gkey(sc)] = self._capture(st, timesteps, sigmas, guidance_scale)
                 # the warm-up pass of a capture advances the state once: restore the initial state
                 st["latents"].copy_(latents, non_blocking=True)
-                st["step"].zero_()
+                st["step"].fill_(start_step)
                 ops.scale_model_input(st["latents"], st["model_in"], sigmas, st["step"])
-        for i in range(steps):
+        for i in range(start_step, steps):
             sc = scale_at(i)
             if self.use_cuda_graph:
                 self._graphs[gkey(sc)].replay()

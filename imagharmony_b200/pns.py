@@ -60,6 +60,21 @@ def gather_scores(local: torch.Tensor, counts: List[int], dist=None) -> torch.Te
     return torch.cat([o[:c].cpu() for o, c in zip(out, counts)])
 
 
+def pns_two_phase(run_preview: Callable[[List[int]], torch.Tensor], run_rest: Callable[[torch.Tensor], torch.Tensor],
+                  seeds: Sequence[int], scorer: Callable, dist=None, max_batch: int = 4) -> "PNSResult":
+    """The inference stage of assets/1.png: every candidate is denoised for a few PREVIEW steps, the judge scores the
+    previews, and only the winner is denoised to the end.
+
+    run_preview(list_of_seeds) -> preview latents [len, C, h, w] (e.g. DenoiseEngine.run(..., stop_after=k));
+    run_rest(preview_latent [1, C, h, w]) -> final latents (DenoiseEngine.run(..., start_step=k)).
+    Collectives: the all_gather of N fp32 scores and one broadcast of the winning preview latent (128 KiB at 1024^2);
+    every rank then finishes the winner redundantly, so all ranks return the same `best_latents` without a third
+    collective (the remaining steps of ONE trajectory do not shard)."""
+    res = pns_select(run_preview, seeds, scorer, dist=dist, max_batch=max_batch, broadcast_winner=True)
+    final = run_rest(res.best_latents.unsqueeze(0))
+    return PNSResult(scores=res.scores, best_index=res.best_index, best_seed=res.best_seed, best_latents=final[0])
+
+
 def pns_select(run_candidates: Callable[[List[int]], torch.Tensor], seeds: Sequence[int], scorer: Callable,
                dist=None, max_batch: int = 4, broadcast_winner: bool = True) -> PNSResult:
     """run_candidates(list_of_seeds) -> final (or preview) latents [len, C, h, w] for those seeds on this rank.

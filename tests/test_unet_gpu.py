@@ -173,6 +173,12 @@ def test_denoise_loop_tiny_matches_oracle(use_graph):
                      control_guidance_end=0.75)
         assert torch.equal(o, o2)
         assert eng.last_launches_per_step > 50
+    # two-phase PNS building blocks: a 2-step preview resumed at step 2 is bit-identical to the uninterrupted run
+    pre = eng.run(latents.pin_memory(), pos, neg, ppool, npool, tid, T, guidance_scale=5.0, ip_scale=0.8,
+                  control_guidance_end=0.75, stop_after=2)
+    res = eng.run(pre, pos, neg, ppool, npool, tid, T, guidance_scale=5.0, ip_scale=0.8, control_guidance_end=0.75,
+                  start_step=2)
+    assert torch.equal(res, o) and not torch.equal(pre, o)
 
 
 def test_adapter_modules_match_reference_goldens_on_gpu():

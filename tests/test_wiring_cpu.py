@@ -94,9 +94,16 @@ def test_native_denoise_loop_wiring_matches_oracle(patched):
     try:
         o = eng.run(latents.clone(), ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T, guidance_scale=5.0, ip_scale=0.6,
                     control_guidance_start=0.3)
+        # two-phase PNS building blocks: a preview (stop_after=k) resumed with start_step=k is the same trajectory
+        pre = eng.run(latents.clone(), ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T, guidance_scale=5.0, ip_scale=0.6,
+                      control_guidance_start=0.3, stop_after=1)
+        res = eng.run(pre, ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T, guidance_scale=5.0, ip_scale=0.6,
+                      control_guidance_start=0.3, start_step=1)
     finally:
         dn.torch.empty = orig_empty
     assert torch.allclose(o, r, rtol=2e-4, atol=2e-4), (o - r).abs().max()
+    assert torch.equal(res, o), "preview + resume must reproduce the uninterrupted trajectory"
+    assert not torch.equal(pre, o)
 
 
 def test_adapter_modules_wiring_matches_reference_goldens(patched):
