@@ -37,7 +37,7 @@ __device__ __forceinline__ void store8(__half* p, const float (&x)[8]) {
 // workspace layout: [GN_MAXB] uint32 tickets at a FIXED offset (so calls with different B never scribble over them;
 // zero once, self-resetting) | floats: [B][GN_MAXG][2*groups] partials | [B][2*groups] mean,rstd
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GN_MAXG = 128;
+constexpr int GN_MAXG = 512;
 constexpr int GN_MAXB = 1024;
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
@@ -306,8 +306,15 @@ extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, 
   int R = 256 / CV;
   if (R < 1) R = 1;
   const int threads = CV * R;
-  // row chunks per image: about two blocks per SM overall, at most GN_MAXG per image
-  int G = (2 * num_sms() + B - 1) / B;
+  // row chunks per image: about `bps` blocks per SM overall, at most GN_MAXG per image.  Measured (tools/gn_probe.py):
+  // at UNet batch 2 the kernels are launch/latency bound and 2 blocks per SM is best; from batch 16 on they are
+  // bandwidth bound and 4 blocks per SM (more loads in flight) is 1.6x faster (64.5 -> 40.6 us at B16 32^2 C1280).
+  static const int bps_env = [] {
+    const char* e = getenv("IH_GN_BLOCKS_PER_SM");
+    return e ? atoi(e) : 0;
+  }();
+  const int bps = bps_env > 0 ? bps_env : (B >= 8 ? 4 : 2);
+  int G = (bps * num_sms() + B - 1) / B;
   if (G > GN_MAXG) G = GN_MAXG;
   int rows_per_block = (HW + G - 1) / G;
   if (rows_per_block < 4 * R) rows_per_block = 4 * R;
