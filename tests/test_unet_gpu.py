@@ -337,3 +337,31 @@ def test_unet_forward_sdxl_base_512_matches_oracle():
     assert torch.isfinite(o).all()
     # ~100 fp16-rounded layers deep: bar = 1 % of the output range and 0.5 % relative RMS against the fp32 oracle
     assert err <= 1e-2 * mx and rel_rms <= 5e-3, (err, mx, rel_rms)
+
+    # BASELINE config 1 end to end: single 512x512 edit, 4 denoise steps (CFG 5.0, IP scale 1.0), native CUDA-graph loop
+    # vs the CPU fp32 oracle loop (custom_pipelines.py:325-363 restated in oracle/scheduler_ref.py)
+    from imagharmony_b200.denoise import DenoiseEngine
+    from oracle.scheduler_ref import denoise_loop, euler_tables, prepare_latents
+    T, n, lat = 4, 1, 64
+    _, _, ins = euler_tables(T)
+    latents = prepare_latents(n, 4, lat, lat, [42], ins)
+    neg, pos = x["ehs"][:n], x["ehs"][n:]
+    npool, ppool = x["text_embeds"][:n], x["text_embeds"][n:]
+    tid = x["time_ids"][:n]
+    ref_procs = [p for p in ref.attn_processors.values() if hasattr(p, "to_k_ip")]
+
+    def set_scale(sc):
+        for p in ref_procs:
+            p.scale = sc
+    with torch.no_grad():
+        fn = lambda s_, t_, e_, te_, ti_: ref(s_.float(), t_, e_, te_, ti_).to(torch.float16)  # noqa: E731
+        r4 = denoise_loop(fn, latents, pos.float(), neg.float(), ppool.float(), npool.float(), tid, T, guidance_scale=5.0,
+                          set_scale=set_scale, conditioning_scale=1.0)
+    o4 = DenoiseEngine(native).run(latents.pin_memory(), pos, neg, ppool, npool, tid, T, guidance_scale=5.0, ip_scale=1.0)
+    torch.cuda.synchronize()
+    d4 = o4.float().cpu() - r4.float()
+    err4, mx4 = d4.abs().max().item(), r4.float().abs().max().item()
+    rms4 = (d4.pow(2).mean().sqrt() / r4.float().pow(2).mean().sqrt()).item()
+    print(f"[C1 trajectory SDXL-base 512^2, 4 steps] max|err| {err4:.3e}  max|ref| {mx4:.3e}  rel-RMS {rms4:.3e}")
+    assert torch.isfinite(o4).all()
+    assert err4 <= 2e-2 * mx4 and rms4 <= 1e-2, (err4, mx4, rms4)
