@@ -364,4 +364,5 @@ def test_unet_forward_sdxl_base_512_matches_oracle():
     rms4 = (d4.pow(2).mean().sqrt() / r4.float().pow(2).mean().sqrt()).item()
     print(f"[C1 trajectory SDXL-base 512^2, 4 steps] max|err| {err4:.3e}  max|ref| {mx4:.3e}  rel-RMS {rms4:.3e}")
     assert torch.isfinite(o4).all()
-    assert err4 <= 2e-2 * mx4 and rms4 <= 1e-2, (err4, mx4, rms4)
+    # measured: max|err| 2.7e-2 on max|ref| 19.4 (1.4e-3 of the range), rel-RMS 1.2e-3
+    assert err4 <= 5e-3 * mx4 and rms4 <= 4e-3, (err4, mx4, rms4)
