@@ -66,3 +66,23 @@ class HarmonyConfig:
 HARMONY_DEFAULT = HarmonyConfig()
 HARMONY_TINY = HarmonyConfig(image_hidden_size=64, text_context_dim=128, inter_dim=256, cross_heads=4,
                              reshape_blocks=4, cross_value_dim=16)
+
+
+@dataclass(frozen=True)
+class VAEConfig:
+    """[3P] diffusers AutoencoderKL of SDXL (decoder half): vae/config.json of stabilityai/stable-diffusion-xl-base-1.0."""
+    latent_channels: int = 4
+    out_channels: int = 3
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    scaling_factor: float = 0.13025
+
+    @property
+    def decoder_channels(self) -> Tuple[int, ...]:
+        return tuple(reversed(self.block_out_channels))
+
+
+SDXL_VAE = VAEConfig()
+# miniature with the same block structure (mid attention, 3 resnets per up block, a channel-changing shortcut)
+TINY_VAE = VAEConfig(block_out_channels=(32, 32, 64, 64), layers_per_block=1, norm_num_groups=8)

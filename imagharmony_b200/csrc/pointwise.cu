@@ -380,6 +380,77 @@ __global__ void mean_tokens_kernel(const __half* __restrict__ x, __half* __restr
   *reinterpret_cast<uint4*>(out + (long long)b * D + c) = o;
 }
 
+// Row softmax in place: x[r, :] <- softmax(x[r, :]) over `cols` fp16 values (fp32 statistics), one block per row, the row
+// held in registers (cols <= 256 threads x 16 vectors x 8 = 32768).  Used by the single-head, head_dim 512 attention
+// of the VAE decoder's mid block (scores = (q / sqrt(d)) k^T from the tensor-core GEMM).
+constexpr int SMX_THREADS = 256;
+constexpr int SMX_MAXV = 16;
+__global__ void __launch_bounds__(SMX_THREADS) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols) {
+  __shared__ float s_red[SMX_THREADS / 32];
+  __shared__ float s_bcast;
+  pdl_launch_dependents();
+  pdl_wait();
+  __half* row = x + (long long)blockIdx.x * ld;
+  const int nv = cols >> 3;
+  float v[SMX_MAXV][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SMX_MAXV; ++i) {
+    const int vi = threadIdx.x + i * SMX_THREADS;
+    if (vi < nv) {
+      ld8(row + vi * 8, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[i][e]);
+    }
+  }
+  auto block_reduce = [&](float val, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, val, o);
+      val = is_max ? fmaxf(val, other) : val + other;
+    }
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = s_red[0];
+      for (int w = 1; w < SMX_THREADS / 32; ++w) r = is_max ? fmaxf(r, s_red[w]) : r + s_red[w];   // fixed order
+      s_bcast = r;
+    }
+    __syncthreads();
+    const float out = s_bcast;
+    __syncthreads();
+    return out;
+  };
+  mx = block_reduce(mx, true);
+  const float ml2 = mx * 1.4426950408889634f;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMX_MAXV; ++i) {
+    const int vi = threadIdx.x + i * SMX_THREADS;
+    if (vi < nv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[i][e] = ex2_approx(fmaf(v[i][e], 1.4426950408889634f, -ml2));
+        sum += v[i][e];
+      }
+    }
+  }
+  sum = block_reduce(sum, false);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < SMX_MAXV; ++i) {
+    const int vi = threadIdx.x + i * SMX_THREADS;
+    if (vi < nv) {
+      uint4 o;
+      o.x = pack_half2(v[i][0] * inv, v[i][1] * inv);
+      o.y = pack_half2(v[i][2] * inv, v[i][3] * inv);
+      o.z = pack_half2(v[i][4] * inv, v[i][5] * inv);
+      o.w = pack_half2(v[i][6] * inv, v[i][7] * inv);
+      *reinterpret_cast<uint4*>(row + vi * 8) = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // The 4-channel ends of the UNet on the tensor-core GEMM:
 //   conv_in : im2col of the NCHW latent -> A [B*H*W, 64] (k = ci*9 + ky*3 + kx, zero padded from 36 to 64 columns),
@@ -556,6 +627,16 @@ extern "C" int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D,
   IH_CHECK(x && out && D % 8 == 0 && n > 0, IH_ERR_ARG, "ih_mean_tokens_f16: bad arguments");
   IH_CUDA(launch_kernel(mean_tokens_kernel, dim3((D / 8 + 127) / 128, B), dim3(128), (size_t)0, (cudaStream_t)stream,
                         (const __half*)x, (__half*)out, n, D));
+  return 0;
+}
+
+extern "C" int ih_softmax_rows_f16(void* x, long long ld, long long rows, int cols, void* stream) {
+  IH_CHECK(x && rows > 0 && cols > 0, IH_ERR_ARG, "ih_softmax_rows_f16: bad arguments");
+  IH_CHECK(cols % 8 == 0 && ld % 8 == 0 && cols <= SMX_THREADS * SMX_MAXV * 8, IH_ERR_SHAPE,
+           "ih_softmax_rows_f16: cols must be a multiple of 8 and <= %d", SMX_THREADS * SMX_MAXV * 8);
+  IH_CHECK(rows <= 0x7fffffffLL, IH_ERR_SHAPE, "ih_softmax_rows_f16: too many rows");
+  IH_CUDA(launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(SMX_THREADS), (size_t)0, (cudaStream_t)stream,
+                        (__half*)x, ld, cols));
   return 0;
 }
 

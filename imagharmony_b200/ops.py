@@ -293,6 +293,16 @@ def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H
     return out
 
 
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dimension of a 2-D fp16 matrix (row stride arbitrary, cols % 8 == 0, <= 32768)."""
+    lib = _lib.load()
+    _req(x, "x")
+    if x.dim() != 2:
+        raise IHError("softmax_rows_: 2-D matrix required")
+    check(lib.ih_softmax_rows_f16(x.data_ptr(), _rows(x, "x"), x.shape[0], x.shape[1], _stream()), "ih_softmax_rows_f16")
+    return x
+
+
 def add_bcast(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a + b where b is broadcast over the leading elements of a (a.numel() % b.numel() == 0), contiguous fp16."""
     lib = _lib.load()

@@ -1,0 +1,244 @@
+"""Native SDXL VAE decoder (scope row f1: custom_pipelines.py:365-386 `vae.decode(latents / scaling_factor)` + postprocess).
+
+Module tree and state-dict keys are those of [3P] diffusers==0.30.0 `AutoencoderKL` (`post_quant_conv.*`, `decoder.*`;
+encoder / quant_conv keys of a full checkpoint are ignored), so `vae/diffusion_pytorch_model.safetensors` loads without
+a key map.  Every operator runs on the sm_100a kernels of this package:
+
+* `post_quant_conv` (1x1, 4->4), the division by `scaling_factor` and `decoder.conv_in` (3x3, 4->C) are ONE tensor-core
+  GEMM: the latent gets a constant-one fifth channel, `ih_im2col3x3_nchw_f16` builds the [B*h*w, 45 -> 64] patch matrix
+  (zero padding applies to the ones channel too, which makes the folded bias exact at the image border) and the folded
+  weight W'[o, (c, tap)] = sum_m conv_in[o, m, tap] * pqc[m, c] / scaling_factor multiplies it;
+* ResnetBlock2D (no time embedding): GroupNorm+SiLU kernel -> implicit-GEMM conv3x3 (residual fused in conv2);
+* mid-block attention (1 head, head_dim = C = 512, N = h*w tokens): fused q|k|v GEMM (1/sqrt(C) folded into q), scores
+  q k^T by the GEMM kernel, `ih_softmax_rows_f16`, P v by the GEMM kernel, out projection with fused residual;
+* nearest 2x upsample + conv3x3; conv_out with Cout padded 3 -> 16 and a gather to NCHW.
+
+Numerics: fp16 storage / fp32 accumulation like the UNet.  The reference upcasts the VAE to fp32 because the ORIGINAL
+SDXL VAE weights overflow in fp16 (custom_pipelines.py:366-371); this decoder is meant for fp16-safe weights (the
+widely used fp16-fix checkpoint) and for the random-init benchmark weights.  A TF32 / split-bf16 variant for the original
+checkpoint is future work.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import IHError
+from .config import SDXL_VAE, VAEConfig
+
+
+class VAEResnetBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, groups: int):
+        super().__init__()
+        self.cin, self.cout, self.groups = cin, cout, groups
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-6)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-6)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self._w1 = self._w2 = self._wsc = None
+
+    def finalize(self):
+        self._w1 = ops.pack_conv3x3_weight(self.conv1.weight.detach())
+        self._w2 = ops.pack_conv3x3_weight(self.conv2.weight.detach())
+        if self.conv_shortcut is not None:
+            self._wsc = self.conv_shortcut.weight.detach().reshape(self.cout, self.cin).contiguous()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, _ = x.shape
+        h = ops.groupnorm(x, self.norm1.weight, self.norm1.bias, groups=self.groups, eps=1e-6, silu=True)
+        h = ops.conv3x3(h, self._w1, self.conv1.bias)
+        h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=1e-6, silu=True)
+        sc = x
+        if self.conv_shortcut is not None:
+            sc = ops.linear(x.reshape(B * H * W, self.cin), self._wsc, self.conv_shortcut.bias).reshape(B, H, W, self.cout)
+        return ops.conv3x3(h, self._w2, self.conv2.bias, residual=sc)
+
+
+class VAEAttention(nn.Module):
+    """diffusers `Attention(heads=1, dim_head=C, norm_num_groups, residual_connection=True, bias=True)`."""
+
+    def __init__(self, ch: int, groups: int):
+        super().__init__()
+        self.ch, self.groups = ch, groups
+        self.group_norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.to_q = nn.Linear(ch, ch)
+        self.to_k = nn.Linear(ch, ch)
+        self.to_v = nn.Linear(ch, ch)
+        self.to_out = nn.ModuleList([nn.Linear(ch, ch), nn.Dropout(0.0)])
+        self._w_qkv = self._b_qkv = None
+
+    def finalize(self):
+        s = self.ch ** -0.5                                      # softmax scale folded into the q projection
+        dt = self.to_q.weight.dtype
+        self._w_qkv = torch.cat([self.to_q.weight.detach().float() * s, self.to_k.weight.detach().float(),
+                                 self.to_v.weight.detach().float()], 0).to(dt).contiguous()
+        self._b_qkv = torch.cat([self.to_q.bias.detach().float() * s, self.to_k.bias.detach().float(),
+                                 self.to_v.bias.detach().float()], 0).to(dt).contiguous()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = x.shape
+        N = H * W
+        if N % 8 != 0 or N > 32768:
+            raise IHError(f"VAE mid-block attention: {N} tokens unsupported (multiple of 8, <= 32768; tile the decode)")
+        h = ops.groupnorm(x, self.group_norm.weight, self.group_norm.bias, groups=self.groups, eps=1e-6, silu=False)
+        qkv = ops.linear(h.reshape(B * N, C), self._w_qkv, self._b_qkv)            # [B*N, 3C]
+        o = torch.empty((B * N, C), dtype=x.dtype, device=x.device)
+        for b in range(B):                                                          # one image at a time: S is N x N
+            rows = slice(b * N, (b + 1) * N)
+            k = qkv[rows, C:2 * C].contiguous()
+            s = ops.linear(qkv[rows, :C], k)                                        # scores (scale already in q)
+            ops.softmax_rows_(s)
+            vt = qkv[rows, 2 * C:].t().contiguous()                                 # [C, N]: right-hand operand of P v
+            ops.linear(s, vt, out=o[rows])
+        out = ops.linear(o, self.to_out[0].weight, self.to_out[0].bias, residual=x.reshape(B * N, C))
+        return out.reshape(B, H, W, C)
+
+
+class VAEUpsample(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+        self._w = None
+
+    def finalize(self):
+        self._w = ops.pack_conv3x3_weight(self.conv.weight.detach())
+
+    def forward(self, x):
+        return ops.conv3x3(ops.upsample2x(x), self._w, self.conv.bias)
+
+
+class VAEMidBlock(nn.Module):
+    def __init__(self, ch: int, groups: int):
+        super().__init__()
+        self.attentions = nn.ModuleList([VAEAttention(ch, groups)])
+        self.resnets = nn.ModuleList([VAEResnetBlock(ch, ch, groups), VAEResnetBlock(ch, ch, groups)])
+
+    def forward(self, x):
+        x = self.resnets[0](x)
+        x = self.attentions[0](x)
+        return self.resnets[1](x)
+
+
+class VAEUpBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, n_res: int, groups: int, add_up: bool):
+        super().__init__()
+        self.resnets = nn.ModuleList([VAEResnetBlock(cin if j == 0 else cout, cout, groups) for j in range(n_res)])
+        if add_up:
+            self.upsamplers = nn.ModuleList([VAEUpsample(cout)])
+        self.has_up = add_up
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        return self.upsamplers[0](x) if self.has_up else x
+
+
+class Decoder(nn.Module):
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        ch = cfg.decoder_channels
+        g = cfg.norm_num_groups
+        self.conv_in = nn.Conv2d(cfg.latent_channels, ch[0], 3, padding=1)
+        self.mid_block = VAEMidBlock(ch[0], g)
+        ups: List[nn.Module] = []
+        prev = ch[0]
+        for i, c in enumerate(ch):
+            ups.append(VAEUpBlock(prev, c, cfg.layers_per_block + 1, g, add_up=i < len(ch) - 1))
+            prev = c
+        self.up_blocks = nn.ModuleList(ups)
+        self.conv_norm_out = nn.GroupNorm(g, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], cfg.out_channels, 3, padding=1)
+
+
+class AutoencoderKLDecoder(nn.Module):
+    """`decode(latents)` = diffusers `vae.decode(latents / scaling_factor).sample` (the division is folded in)."""
+
+    def __init__(self, cfg: VAEConfig = SDXL_VAE):
+        super().__init__()
+        self.config = cfg
+        self.post_quant_conv = nn.Conv2d(cfg.latent_channels, cfg.latent_channels, 1)
+        self.decoder = Decoder(cfg)
+        self._w_in = self._w_out = self._b_out = None
+
+    # ---- construction ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, cfg: VAEConfig, sd: Dict[str, torch.Tensor], device="cuda") -> "AutoencoderKLDecoder":
+        with torch.device("meta"):
+            m = cls(cfg)
+        m = m.to_empty(device=device)
+        own = m.state_dict()
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise KeyError(f"VAE checkpoint lacks {len(missing)} decoder keys, e.g. {missing[:3]}")
+        m.load_state_dict({k: sd[k].to(device=device, dtype=torch.float16).reshape(own[k].shape) for k in own})
+        m = m.half().eval()
+        m.finalize()
+        return m
+
+    def finalize(self) -> None:
+        for mod in self.modules():
+            if isinstance(mod, (VAEResnetBlock, VAEAttention, VAEUpsample)):
+                mod.finalize()
+        cfg = self.config
+        L = cfg.latent_channels
+        w_in = self.decoder.conv_in.weight.detach().float()                          # [C, L, 3, 3]
+        w_pq = self.post_quant_conv.weight.detach().float().reshape(L, L)            # [m, c]
+        b_pq = self.post_quant_conv.bias.detach().float()
+        C0 = w_in.shape[0]
+        folded = torch.zeros((C0, L + 1, 9), dtype=torch.float32, device=w_in.device)
+        wt = w_in.reshape(C0, L, 9)                                                  # [o, m, tap]
+        folded[:, :L] = torch.einsum("omt,mc->oct", wt, w_pq) / cfg.scaling_factor   # latent channels (z / sf folded)
+        folded[:, L] = torch.einsum("omt,m->ot", wt, b_pq)                           # the constant-one channel
+        kpad = 64
+        w = torch.zeros((C0, kpad), dtype=torch.float32, device=w_in.device)
+        w[:, :(L + 1) * 9] = folded.reshape(C0, (L + 1) * 9)                         # k = ci*9 + ky*3 + kx
+        self._w_in = w.to(self.decoder.conv_in.weight.dtype).contiguous()
+        co = self.decoder.conv_out
+        cpad = 16
+        w_out = torch.zeros((cpad,) + tuple(co.weight.shape[1:]), dtype=co.weight.dtype, device=co.weight.device)
+        w_out[:cfg.out_channels] = co.weight.detach()
+        self._w_out = ops.pack_conv3x3_weight(w_out)
+        b_out = torch.zeros((cpad,), dtype=co.weight.dtype, device=co.weight.device)
+        b_out[:cfg.out_channels] = co.bias.detach()
+        self._b_out = b_out
+
+    # ---- forward -----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def decode(self, latents: torch.Tensor) -> torch.Tensor:
+        """latents [B, 4, h, w] fp16 straight from the denoise loop -> image [B, 3, 8h, 8w] fp16 in [-1, 1] (nominally)."""
+        if self._w_in is None:
+            raise IHError("AutoencoderKLDecoder.finalize() has not run (use from_state_dict)")
+        B, L, h, w = latents.shape
+        dec = self.decoder
+        dt = self._w_in.dtype                                     # fp16 on the GPU (fp32 only in the CPU wiring test)
+        ones = torch.ones((B, 1, h, w), dtype=dt, device=latents.device)
+        z5 = torch.cat([latents.to(dt), ones], dim=1).contiguous()
+        a = ops.im2col3x3_nchw(z5, self._w_in.shape[1])
+        x = ops.linear(a, self._w_in, dec.conv_in.bias).reshape(B, h, w, -1)           # post_quant_conv + /sf + conv_in
+        x = dec.mid_block(x)
+        for blk in dec.up_blocks:
+            x = blk(x)
+        g = self.config.norm_num_groups
+        x = ops.groupnorm(x, dec.conv_norm_out.weight, dec.conv_norm_out.bias, groups=g, eps=1e-6, silu=True)
+        x = ops.conv3x3(x, self._w_out, self._b_out)
+        return ops.nhwc_to_nchw(x, self.config.out_channels)
+
+
+def postprocess(image: torch.Tensor, output_type: str = "pil"):
+    """[3P] diffusers VaeImageProcessor.postprocess as used at custom_pipelines.py:383: denormalise to [0, 1], NHWC,
+    uint8 rounding, PIL.  `output_type` in {"pt", "np", "pil"}."""
+    img = (image.float() / 2 + 0.5).clamp(0, 1)
+    if output_type == "pt":
+        return img
+    arr = img.permute(0, 2, 3, 1).cpu().numpy()
+    if output_type == "np":
+        return arr
+    if output_type != "pil":
+        raise IHError(f"unknown output_type {output_type!r}")
+    from PIL import Image
+    u8 = (arr * 255).round().astype("uint8")
+    return [Image.fromarray(a) for a in u8]

@@ -137,6 +137,11 @@ int ih_add_bcast_f16(const void* a, const void* b, void* out, long long n, long 
 /* out[b, :] = mean_n x[b, n, :]  -- Resampler masked_mean with an all-ones mask (resampler.py:137-138,150-158). */
 int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D, void* stream);
 
+/* In-place row softmax of an fp16 matrix [rows, cols] (row stride ld elements, fp32 statistics), cols <= 32768.  With
+ * two ih_gemm_f16 calls it forms the single-head, head_dim-512 attention of the VAE decoder mid block
+ * ([3P] diffusers AutoencoderKL, called at custom_pipelines.py:373). */
+int ih_softmax_rows_f16(void* x, long long ld, long long rows, int cols, void* stream);
+
 /* Nearest-neighbour 2x upsample NHWC [B,H,W,C] -> [B,2H,2W,C]. */
 int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream);
 

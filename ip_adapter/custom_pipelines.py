@@ -7,8 +7,9 @@ a dependency here, so the pieces the reference touches are provided directly:
 
 Denoise loop semantics follow custom_pipelines.py:188-363 (CFG batch [negative, positive], per-step IP-scale gating
 by control_guidance_start/end, Euler update); the loop itself runs as replayed CUDA graphs (imagharmony_b200/denoise.py).
-VAE decode / PIL post-processing (:365-386) is the "next" row of the scope table: pass output_type="latent" or give the
-pipeline a `vae_decode` callable.
+VAE decode / PIL post-processing (:365-386, scope row f1) runs on the native decoder `imagharmony_b200.vae` when the
+pipeline owns one (`from_random`, or `from_pretrained` with a `vae/` folder); a `vae_decode` callable overrides it and
+`output_type="latent"` skips it.
 """
 from __future__ import annotations
 
@@ -59,8 +60,10 @@ class StableDiffusionXLCustomPipeline:
     vae_scale_factor = 8
 
     def __init__(self, unet: UNet2DConditionModel, prompt_encoder: Optional[Callable] = None,
-                 vae_decode: Optional[Callable] = None, scheduler: Optional[EulerDiscreteScheduler] = None):
+                 vae_decode: Optional[Callable] = None, scheduler: Optional[EulerDiscreteScheduler] = None,
+                 vae=None):
         self.unet = unet
+        self.vae = vae                      # imagharmony_b200.vae.AutoencoderKLDecoder or None
         self.scheduler = scheduler or EulerDiscreteScheduler()
         self.prompt_encoder = prompt_encoder or SyntheticPromptEncoder(unet.config)
         self.vae_decode = vae_decode
@@ -70,14 +73,21 @@ class StableDiffusionXLCustomPipeline:
 
     # ---- construction ------------------------------------------------------------------------------------------
     @classmethod
-    def from_random(cls, cfg: UNetConfig = SDXL_BASE, seed: int = 0, device="cuda"):
+    def from_random(cls, cfg: UNetConfig = SDXL_BASE, seed: int = 0, device="cuda", vae_cfg=None):
         """Random-init weights of the given architecture (the benchmark / test configuration)."""
         from imagharmony_b200.weights import random_state_dict, shapes_of
         with torch.device("meta"):
             shapes = shapes_of(UNet2DConditionModel(cfg))
         gen_dev = device if str(device).startswith("cuda") else "cpu"
         unet = UNet2DConditionModel.from_state_dict(cfg, random_state_dict(shapes, seed, device=gen_dev), device=device)
-        return cls(unet)
+        vae = None
+        if vae_cfg is not None:
+            from imagharmony_b200.vae import AutoencoderKLDecoder
+            with torch.device("meta"):
+                vshapes = shapes_of(AutoencoderKLDecoder(vae_cfg))
+            vae = AutoencoderKLDecoder.from_state_dict(vae_cfg, random_state_dict(vshapes, seed + 17, device=gen_dev),
+                                                       device=device)
+        return cls(unet, vae=vae)
 
     @classmethod
     def from_pretrained(cls, path: str, torch_dtype=torch.float16, add_watermarker: bool = False, device="cuda",
@@ -91,7 +101,15 @@ class StableDiffusionXLCustomPipeline:
         if not os.path.exists(f):
             raise FileNotFoundError(f"no SDXL UNet weights under {path}/unet (safetensors)")
         unet = UNet2DConditionModel.from_state_dict(SDXL_BASE, load_file(f), device=device)
-        return cls(unet)
+        vae = None
+        for name in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors"):
+            vf = os.path.join(path, "vae", name)
+            if os.path.exists(vf):
+                from imagharmony_b200.config import SDXL_VAE
+                from imagharmony_b200.vae import AutoencoderKLDecoder
+                vae = AutoencoderKLDecoder.from_state_dict(SDXL_VAE, load_file(vf), device=device)   # decoder keys only
+                break
+        return cls(unet, vae=vae)
 
     def to(self, device=None, *args, **kwargs):
         return self      # weights already live on the device the UNet was built on
@@ -195,10 +213,14 @@ class StableDiffusionXLCustomPipeline:
         if output_type == "latent":
             image = out
         else:
-            if self.vae_decode is None:
-                raise IHError("VAE decode is outside this hot path (scope table row f1): call with "
-                              "output_type='latent' or construct the pipeline with a vae_decode callable")
-            image = self.vae_decode(out / 0.13025, output_type)                       # :373 (scaling_factor [3P])
+            if self.vae_decode is not None:
+                image = self.vae_decode(out / 0.13025, output_type)                   # :373 (scaling_factor [3P])
+            elif self.vae is not None:
+                from imagharmony_b200.vae import postprocess
+                image = postprocess(self.vae.decode(out), output_type)                # :373 + :383 (/ scaling_factor folded)
+            else:
+                raise IHError("this pipeline has no VAE decoder: call with output_type='latent', build it with a `vae` "
+                              "(from_random(vae_cfg=...), from_pretrained with a vae/ folder) or pass a vae_decode callable")
         if not return_dict:
             return (image,)
         return StableDiffusionXLPipelineOutput(images=image)

@@ -1,0 +1,46 @@
+"""CPU wiring test of the native VAE decoder (scope row f1): layouts, the folded post_quant_conv / scaling / conv_in
+GEMM (incl. the constant-one channel that makes the folded bias exact at the border), the GEMM-softmax-GEMM mid-block
+attention, up-block order and the padded conv_out, against the fp32 oracle with stand-in ops (no kernels involved)."""
+import numpy as np
+import torch
+
+from test_wiring_cpu import patched  # noqa: F401  (fixture)
+
+
+def _pair(cfg, seed=0):
+    from imagharmony_b200.vae import AutoencoderKLDecoder
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    from oracle.vae_ref import VAEDecoderRef
+    with torch.device("meta"):
+        shapes = shapes_of(VAEDecoderRef(cfg))
+    sd = {k: v.float() for k, v in random_state_dict(shapes, seed).items()}
+    ref = VAEDecoderRef(cfg)
+    ref.load_state_dict(sd)
+    with torch.device("meta"):
+        native = AutoencoderKLDecoder(cfg)
+    native.load_state_dict(sd, assign=True)
+    native.finalize()
+    return native, ref.eval()
+
+
+def test_vae_decoder_wiring_matches_oracle(patched):  # noqa: F811
+    from imagharmony_b200.config import TINY_VAE
+    native, ref = _pair(TINY_VAE, seed=3)
+    assert list(native.state_dict().keys()) == list(ref.state_dict().keys())      # diffusers key contract
+    z = torch.randn(2, 4, 4, 4, generator=torch.Generator().manual_seed(1)) * TINY_VAE.scaling_factor * 3
+    with torch.no_grad():
+        r = ref.decode(z)
+        o = native.decode(z)
+    assert o.shape == r.shape == (2, 3, 32, 32)
+    assert torch.allclose(o, r, rtol=1e-4, atol=1e-4), (o - r).abs().max()
+
+
+def test_vae_postprocess_matches_reference_semantics():
+    from imagharmony_b200.vae import postprocess
+    from oracle.vae_ref import postprocess_ref
+    img = torch.randn(2, 3, 16, 16) * 1.5
+    np.testing.assert_allclose(postprocess(img, "np"), postprocess_ref(img), rtol=0, atol=0)
+    pil = postprocess(img, "pil")
+    assert len(pil) == 2 and pil[0].size == (16, 16) and pil[0].mode == "RGB"
+    u8 = np.asarray(pil[1])
+    assert np.array_equal(u8, (postprocess_ref(img)[1] * 255).round().astype("uint8"))

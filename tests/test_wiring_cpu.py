@@ -160,7 +160,8 @@ def test_ip_adapter_xl_generate_call_surface(patched, tmp_path):
     from train import HarmonyAttention as HA2                                  # test.py:5 import path
     assert HA2 is HarmonyAttention and ComposedAttention is HarmonyAttention
 
-    pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu")
+    from imagharmony_b200.config import TINY_VAE
+    pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu", vae_cfg=TINY_VAE)
     assert not hasattr(pipe, "controlnet")
     h = HARMONY_TINY
     ha = HarmonyAttention(image_hidden_size=h.image_hidden_size, text_context_dim=h.text_context_dim,
@@ -192,5 +193,9 @@ def test_ip_adapter_xl_generate_call_surface(patched, tmp_path):
     # extra_text=None is tolerated (the reference raises NameError there)
     ip_model.generate(pil_image=None, clip_image_embeds=img, num_samples=1, num_inference_steps=1, seed=1,
                       output_type="latent", height=128, width=128)
+    # the reference's default: PIL images out of the VAE decoder + postprocess (ip_adapter.py:330-340, test.py:33-41)
+    pil = ip_model.generate(pil_image=None, clip_image_embeds=img, prompt="lions", num_samples=2, num_inference_steps=1,
+                            seed=[3, 4], extra_text="eight sheep", height=128, width=128)
+    assert isinstance(pil, list) and len(pil) == 2 and pil[0].size == (128, 128) and pil[0].mode == "RGB"
     ip_model.set_scale(0.25)
     assert all(p.scale == 0.25 for p in pipe.unet.attn_processors.values() if hasattr(p, "to_k_ip"))
