@@ -84,5 +84,6 @@ class VAEConfig:
 
 
 SDXL_VAE = VAEConfig()
-# miniature with the same block structure (mid attention, 3 resnets per up block, a channel-changing shortcut)
-TINY_VAE = VAEConfig(block_out_channels=(32, 32, 64, 64), layers_per_block=1, norm_num_groups=8)
+# miniature with the same block structure (mid attention, a channel-changing shortcut); channels stay multiples of 64
+# because the implicit-GEMM conv kernel needs Cin % 64 == 0
+TINY_VAE = VAEConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=1, norm_num_groups=8)
