@@ -166,6 +166,12 @@ def cpu_unet_seconds(lat: int, repeats: int, warm: int, budget_s: float = 60.0):
     return times[len(times) // 2], len(times)
 
 
+def workload_string(res: int, steps: int, images: int) -> str:
+    """The one workload both arms report (BASELINE config 2 by default)."""
+    return (f"single {res}x{res} edit per GPU, {steps}-step Euler schedule, {images} image(s)/GPU (UNet batch "
+            f"{2 * images}), SDXL-base UNet random-init, 77+4 tokens, guidance 5.0, IP scale 1.0")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,7 +192,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": est_step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"single {args.res}x{args.res} edit, {args.steps}-step schedule, {args.images} image(s)"},
+            "config": {"workload": workload_string(args.res, args.steps, args.images),
+                       "note": "same workload as the native arm; measured on a bounded CPU sample (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": value, "unit": "denoise-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -388,9 +395,7 @@ def main():
             "metric": METRIC, "value": world * n * K / dev_s, "unit": "denoise-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"single {args.res}x{args.res} edit per GPU, {K}-step Euler schedule, "
-                                   f"{n} image(s)/GPU (UNet batch {2 * n}), SDXL-base UNet random-init, 77+4 tokens, "
-                                   f"guidance 5.0, IP scale 1.0",
+            "config": {"workload": workload_string(args.res, K, n),
                        "l2": "per-step working set (5.2 GB weights) exceeds L2; inputs larger than L2",
                        "step_tflop_algorithmic": step_tflop,
                        "step_tflops_achieved": step_tflop * K / dev_s,
