@@ -58,6 +58,7 @@ class SyntheticPromptEncoder:
 
 class StableDiffusionXLCustomPipeline:
     vae_scale_factor = 8
+    force_zeros_for_empty_prompt = True     # [3P] SDXL-base pipeline config
 
     def __init__(self, unet: UNet2DConditionModel, prompt_encoder: Optional[Callable] = None,
                  vae_decode: Optional[Callable] = None, scheduler: Optional[EulerDiscreteScheduler] = None,
@@ -109,7 +110,11 @@ class StableDiffusionXLCustomPipeline:
                 from imagharmony_b200.vae import AutoencoderKLDecoder
                 vae = AutoencoderKLDecoder.from_state_dict(SDXL_VAE, load_file(vf), device=device)   # decoder keys only
                 break
-        return cls(unet, vae=vae)
+        enc = None
+        from .encoders import ClipPromptEncoder
+        if ClipPromptEncoder.available(path):
+            enc = ClipPromptEncoder.from_pretrained(path, device=device, dtype=torch_dtype)
+        return cls(unet, prompt_encoder=enc, vae=vae)
 
     def to(self, device=None, *args, **kwargs):
         return self      # weights already live on the device the UNet was built on
@@ -140,7 +145,12 @@ class StableDiffusionXLCustomPipeline:
             prompt_embeds, pooled_prompt_embeds = self.prompt_encoder(prompts)
             prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
             pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
-        if do_classifier_free_guidance and negative_prompt_embeds is None:
+        if do_classifier_free_guidance and negative_prompt_embeds is None and negative_prompt is None \
+                and self.force_zeros_for_empty_prompt:
+            # [3P] SDXL-base model_index.json: force_zeros_for_empty_prompt = true -> no negative prompt means ZERO embeds
+            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+            negative_pooled_prompt_embeds = torch.zeros_like(pooled_prompt_embeds)
+        elif do_classifier_free_guidance and negative_prompt_embeds is None:
             negs = negative_prompt if negative_prompt is not None else ""
             negs = [negs] * (prompt_embeds.shape[0] // num_images_per_prompt) if isinstance(negs, str) else list(negs)
             negative_prompt_embeds, negative_pooled_prompt_embeds = self.prompt_encoder(negs)
