@@ -77,6 +77,12 @@ class VAEConfig:
     layers_per_block: int = 2
     norm_num_groups: int = 32
     scaling_factor: float = 0.13025
+    sample_size: int = 1024               # tiling: tiles of sample_size pixels (= sample_size / 8 latents), 25 % overlap
+    tile_overlap_factor: float = 0.25
+
+    @property
+    def tile_latent_min_size(self) -> int:
+        return int(self.sample_size / (2 ** (len(self.block_out_channels) - 1)))
 
     @property
     def decoder_channels(self) -> Tuple[int, ...]:
@@ -86,4 +92,4 @@ class VAEConfig:
 SDXL_VAE = VAEConfig()
 # miniature with the same block structure (mid attention, a channel-changing shortcut); channels stay multiples of 64
 # because the implicit-GEMM conv kernel needs Cin % 64 == 0
-TINY_VAE = VAEConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=1, norm_num_groups=8)
+TINY_VAE = VAEConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=1, norm_num_groups=8, sample_size=64)

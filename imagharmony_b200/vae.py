@@ -82,18 +82,30 @@ class VAEAttention(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
         N = H * W
-        if N % 8 != 0 or N > 32768:
-            raise IHError(f"VAE mid-block attention: {N} tokens unsupported (multiple of 8, <= 32768; tile the decode)")
+        Np = (N + 7) // 8 * 8                 # the GEMM / softmax kernels want multiples of 8: pad keys, mask their scores
+        if Np > 32768:
+            raise IHError(f"VAE mid-block attention: {N} tokens exceed 32768 (enable_vae_tiling() decodes 128x128 tiles)")
         h = ops.groupnorm(x, self.group_norm.weight, self.group_norm.bias, groups=self.groups, eps=1e-6, silu=False)
         qkv = ops.linear(h.reshape(B * N, C), self._w_qkv, self._b_qkv)            # [B*N, 3C]
         o = torch.empty((B * N, C), dtype=x.dtype, device=x.device)
         for b in range(B):                                                          # one image at a time: S is N x N
             rows = slice(b * N, (b + 1) * N)
-            k = qkv[rows, C:2 * C].contiguous()
-            s = ops.linear(qkv[rows, :C], k)                                        # scores (scale already in q)
+            if Np == N:
+                q = qkv[rows, :C]
+                k = qkv[rows, C:2 * C].contiguous()
+                vt = qkv[rows, 2 * C:].t().contiguous()                             # [C, N]: right-hand operand of P v
+            else:                                                                   # odd edge tiles of a tiled decode
+                pad = torch.zeros((Np, 3 * C), dtype=x.dtype, device=x.device)
+                pad[:N] = qkv[rows]
+                q, k, vt = pad[:, :C], pad[:, C:2 * C].contiguous(), pad[:, 2 * C:].t().contiguous()
+            s = ops.linear(q, k)                                                    # scores (scale already in q)
+            if Np != N:
+                s[:, N:] = float("-inf")                                            # padded keys get no weight
             ops.softmax_rows_(s)
-            vt = qkv[rows, 2 * C:].t().contiguous()                                 # [C, N]: right-hand operand of P v
-            ops.linear(s, vt, out=o[rows])
+            if Np == N:
+                ops.linear(s, vt, out=o[rows])
+            else:
+                o[rows] = ops.linear(s, vt)[:N]
         out = ops.linear(o, self.to_out[0].weight, self.to_out[0].bias, residual=x.reshape(B * N, C))
         return out.reshape(B, H, W, C)
 
@@ -163,6 +175,7 @@ class AutoencoderKLDecoder(nn.Module):
         self.post_quant_conv = nn.Conv2d(cfg.latent_channels, cfg.latent_channels, 1)
         self.decoder = Decoder(cfg)
         self._w_in = self._w_out = self._b_out = None
+        self.use_tiling = False             # pipeline.enable_vae_tiling() (test.py:73)
 
     # ---- construction ------------------------------------------------------------------------------------------
     @classmethod
@@ -209,9 +222,55 @@ class AutoencoderKLDecoder(nn.Module):
     # ---- forward -----------------------------------------------------------------------------------------------
     @torch.no_grad()
     def decode(self, latents: torch.Tensor) -> torch.Tensor:
-        """latents [B, 4, h, w] fp16 straight from the denoise loop -> image [B, 3, 8h, 8w] fp16 in [-1, 1] (nominally)."""
+        """latents [B, 4, h, w] fp16 straight from the denoise loop -> image [B, 3, 8h, 8w] fp16 in [-1, 1] (nominally).
+        With `use_tiling` and a latent larger than one tile (128 x 128 for SDXL) the image is decoded tile by tile and
+        blended, [3P] diffusers `AutoencoderKL.tiled_decode`."""
         if self._w_in is None:
             raise IHError("AutoencoderKLDecoder.finalize() has not run (use from_state_dict)")
+        t = self.config.tile_latent_min_size
+        if self.use_tiling and (latents.shape[-1] > t or latents.shape[-2] > t):
+            return self._tiled_decode(latents)
+        return self._decode_tile(latents)
+
+    def _tiled_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """[3P] tiled_decode: tiles of `tile_latent_min_size` latents every (1 - overlap) tile, each decoded on its own
+        (so tile borders see zero padding, as in diffusers), then linearly cross-faded over the overlap with the tile
+        above and the tile to the left and cropped to the stride.  The cross-fade is elementwise torch glue."""
+        cfg = self.config
+        tl = cfg.tile_latent_min_size
+        overlap = int(tl * (1 - cfg.tile_overlap_factor))
+        blend = int(cfg.sample_size * cfg.tile_overlap_factor)
+        limit = cfg.sample_size - blend
+        rows = []
+        for i in range(0, z.shape[2], overlap):
+            rows.append([self._decode_tile(z[:, :, i:i + tl, j:j + tl].contiguous()).float()
+                         for j in range(0, z.shape[3], overlap)])
+
+        def blend_v(a, b, ext):
+            ext = min(a.shape[2], b.shape[2], ext)
+            wgt = (torch.arange(ext, device=b.device, dtype=torch.float32) / ext).view(1, 1, ext, 1)
+            b[:, :, :ext, :] = a[:, :, -ext:, :] * (1 - wgt) + b[:, :, :ext, :] * wgt
+            return b
+
+        def blend_h(a, b, ext):
+            ext = min(a.shape[3], b.shape[3], ext)
+            wgt = (torch.arange(ext, device=b.device, dtype=torch.float32) / ext).view(1, 1, 1, ext)
+            b[:, :, :, :ext] = a[:, :, :, -ext:] * (1 - wgt) + b[:, :, :, :ext] * wgt
+            return b
+
+        out_rows = []
+        for i, row in enumerate(rows):
+            out_row = []
+            for j, tile in enumerate(row):
+                if i > 0:
+                    tile = blend_v(rows[i - 1][j], tile, blend)
+                if j > 0:
+                    tile = blend_h(row[j - 1], tile, blend)
+                out_row.append(tile[:, :, :limit, :limit])
+            out_rows.append(torch.cat(out_row, dim=3))
+        return torch.cat(out_rows, dim=2).to(z.dtype if z.dtype != torch.float32 else torch.float32)
+
+    def _decode_tile(self, latents: torch.Tensor) -> torch.Tensor:
         B, L, h, w = latents.shape
         dec = self.decoder
         dt = self._w_in.dtype                                     # fp16 on the GPU (fp32 only in the CPU wiring test)

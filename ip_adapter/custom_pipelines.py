@@ -120,7 +120,8 @@ class StableDiffusionXLCustomPipeline:
         return self      # weights already live on the device the UNet was built on
 
     def enable_vae_tiling(self):  # test.py:73
-        return None
+        if self.vae is not None:
+            self.vae.use_tiling = True
 
     # ---- reference surface -------------------------------------------------------------------------------------
     def set_scale(self, scale):

@@ -116,3 +116,38 @@ class VAEDecoderRef(nn.Module):
 def postprocess_ref(image: torch.Tensor):
     """VaeImageProcessor.postprocess(output_type='np'): (x / 2 + 0.5).clamp(0, 1) -> NHWC float numpy"""
     return (image.float() / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).cpu().numpy()
+
+
+def tiled_decode_ref(vae: "VAEDecoderRef", latents: torch.Tensor) -> torch.Tensor:
+    """[3P] AutoencoderKL.tiled_decode (test.py:73 `pipe.enable_vae_tiling()`): 25 % overlapping tiles of
+    tile_latent_min_size latents, each through post_quant_conv + decoder on its own, blended with the upper and the left
+    neighbour over `blend_extent` pixels and cropped to `row_limit`."""
+    cfg = vae.config
+    z = latents / cfg.scaling_factor
+    tl = cfg.tile_latent_min_size
+    overlap_size = int(tl * (1 - cfg.tile_overlap_factor))
+    blend_extent = int(cfg.sample_size * cfg.tile_overlap_factor)
+    row_limit = cfg.sample_size - blend_extent
+    rows = []
+    for i in range(0, z.shape[2], overlap_size):
+        row = []
+        for j in range(0, z.shape[3], overlap_size):
+            row.append(vae.decoder(vae.post_quant_conv(z[:, :, i:i + tl, j:j + tl])))
+        rows.append(row)
+    result_rows = []
+    for i, row in enumerate(rows):
+        result_row = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                a, b = rows[i - 1][j], tile
+                ext = min(a.shape[2], b.shape[2], blend_extent)
+                for y in range(ext):
+                    b[:, :, y, :] = a[:, :, -ext + y, :] * (1 - y / ext) + b[:, :, y, :] * (y / ext)
+            if j > 0:
+                a, b = row[j - 1], tile
+                ext = min(a.shape[3], b.shape[3], blend_extent)
+                for x in range(ext):
+                    b[:, :, :, x] = a[:, :, :, -ext + x] * (1 - x / ext) + b[:, :, :, x] * (x / ext)
+            result_row.append(tile[:, :, :row_limit, :row_limit])
+        result_rows.append(torch.cat(result_row, dim=3))
+    return torch.cat(result_rows, dim=2)

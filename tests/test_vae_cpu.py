@@ -44,3 +44,21 @@ def test_vae_postprocess_matches_reference_semantics():
     assert len(pil) == 2 and pil[0].size == (16, 16) and pil[0].mode == "RGB"
     u8 = np.asarray(pil[1])
     assert np.array_equal(u8, (postprocess_ref(img)[1] * 255).round().astype("uint8"))
+
+
+def test_vae_tiled_decode_matches_oracle(patched):  # noqa: F811
+    """pipe.enable_vae_tiling() (test.py:73): a latent larger than one tile is decoded tile-wise and cross-faded like
+    [3P] AutoencoderKL.tiled_decode; a latent that fits one tile takes the plain path."""
+    from imagharmony_b200.config import TINY_VAE            # sample_size 64 -> 8 x 8 latent tiles, stride 6, blend 16 px
+    from oracle.vae_ref import tiled_decode_ref
+    native, ref = _pair(TINY_VAE, seed=4)
+    native.use_tiling = True
+    z = torch.randn(1, 4, 14, 11, generator=torch.Generator().manual_seed(2)) * TINY_VAE.scaling_factor * 3
+    with torch.no_grad():
+        r = tiled_decode_ref(ref, z)
+        o = native.decode(z)
+    assert o.shape == r.shape
+    assert torch.allclose(o, r, rtol=1e-4, atol=1e-4), (o - r).abs().max()
+    small = z[:, :, :8, :8].contiguous()
+    with torch.no_grad():
+        assert torch.allclose(native.decode(small), ref.decode(small), rtol=1e-4, atol=1e-4)

@@ -72,3 +72,21 @@ def test_vae_decoder_sdxl_256_matches_oracle_and_postprocess():
     r8 = (postprocess_ref(r)[0] * 255).round().astype(np.int32)
     assert u8.shape == (256, 256, 3)
     assert np.abs(u8 - r8).max() <= 1, np.abs(u8 - r8).max()
+
+
+def test_vae_tiled_decode_matches_oracle():
+    """enable_vae_tiling (test.py:73): overlapping 8x8-latent tiles of the miniature VAE incl. ragged edge tiles (token
+    counts that are not multiples of 8 -> padded keys with -inf scores) against the oracle's tiled_decode."""
+    from imagharmony_b200.config import TINY_VAE
+    from oracle.vae_ref import tiled_decode_ref
+    native, ref32, _ = _models(TINY_VAE, seed=9)
+    native.use_tiling = True
+    z = (torch.randn(1, 4, 14, 11, generator=torch.Generator("cpu").manual_seed(3)) * TINY_VAE.scaling_factor * 2).half()
+    with torch.no_grad():
+        r = tiled_decode_ref(ref32, z.float())
+        o = native.decode(z.cuda()).float().cpu()
+    torch.cuda.synchronize()
+    err, mx = (o - r).abs().max().item(), r.abs().max().item()
+    print(f"[vae tiled] max|err| {err:.3e} max|ref| {mx:.3e}")
+    assert o.shape == r.shape and torch.isfinite(o).all()
+    assert err <= 1e-2 * mx, (err, mx)
