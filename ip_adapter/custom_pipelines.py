@@ -92,7 +92,7 @@ class StableDiffusionXLCustomPipeline:
 
     @classmethod
     def from_pretrained(cls, path: str, torch_dtype=torch.float16, add_watermarker: bool = False, device="cuda",
-                        **kwargs):
+                        cfg: UNetConfig = SDXL_BASE, vae_cfg=None, **kwargs):
         """test.py:68-72.  Loads `<path>/unet/diffusion_pytorch_model.safetensors` (diffusers key names are the native
         UNet's key names, so no key map is needed)."""
         from safetensors.torch import load_file
@@ -101,14 +101,14 @@ class StableDiffusionXLCustomPipeline:
             f = os.path.join(path, "unet", "diffusion_pytorch_model.fp16.safetensors")
         if not os.path.exists(f):
             raise FileNotFoundError(f"no SDXL UNet weights under {path}/unet (safetensors)")
-        unet = UNet2DConditionModel.from_state_dict(SDXL_BASE, load_file(f), device=device)
+        unet = UNet2DConditionModel.from_state_dict(cfg, load_file(f), device=device)
         vae = None
         for name in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors"):
             vf = os.path.join(path, "vae", name)
             if os.path.exists(vf):
                 from imagharmony_b200.config import SDXL_VAE
                 from imagharmony_b200.vae import AutoencoderKLDecoder
-                vae = AutoencoderKLDecoder.from_state_dict(SDXL_VAE, load_file(vf), device=device)   # decoder keys only
+                vae = AutoencoderKLDecoder.from_state_dict(vae_cfg or SDXL_VAE, load_file(vf), device=device)  # decoder keys only
                 break
         enc = None
         from .encoders import ClipPromptEncoder
