@@ -14,7 +14,6 @@ the forward-time prints of HarmonyAttention are dropped (C.10); one copy of the 
 from __future__ import annotations
 
 import os
-from typing import List, Optional
 
 import torch
 from PIL import Image
@@ -31,14 +30,47 @@ else:  # pragma: no cover
     from .attention_processor import AttnProcessor, IPAttnProcessor
 
 
+DEFAULT_PROMPT = "best quality, high quality"                                           # reference :276, :441
+DEFAULT_NEGATIVE_PROMPT = "monochrome, lowres, bad anatomy, worst quality, low quality"     # reference :278, :443
+IP_LAYER_MARKER = "down_blocks.2.attentions.1"   # the only attn2 layers whose IP branch is active (reference :117)
+
+# prefixes under which the three parts of an adapter checkpoint appear in a flat (.safetensors / accelerate) file
+_CKPT_PREFIXES = (("image_proj.", "image_proj"), ("image_proj_model.", "image_proj"), ("ip_adapter.", "ip_adapter"),
+                  ("adapter_modules.", "ip_adapter"), ("composed_adapter.", "composed_adapter"),
+                  ("composed_modules.", "composed_adapter"))
+
+
+def _block_channels(proc_name: str, channels) -> int:
+    """Width of the attention module a processor name belongs to (`<down|up>_blocks.<i>...` / `mid_block...`)."""
+    head, _, rest = proc_name.partition(".")
+    if head == "mid_block":
+        return channels[-1]
+    level = int(rest.split(".", 1)[0])
+    if head == "up_blocks":
+        return channels[len(channels) - 1 - level]
+    if head == "down_blocks":
+        return channels[level]
+    raise IHError(f"unexpected attention processor name {proc_name!r}")
+
+
+def _per_image(value, default, count):
+    """prompt / negative_prompt argument -> one string per input image"""
+    value = default if value is None else value
+    return list(value) if isinstance(value, (list, tuple)) else [value] * count
+
+
+def _repeat_for_samples(t: torch.Tensor, num_samples: int) -> torch.Tensor:
+    """[b, n, d] -> [b * num_samples, n, d], the copies of one image adjacent (reference :302-306)"""
+    b, n, d = t.shape
+    return t.unsqueeze(1).expand(b, num_samples, n, d).reshape(b * num_samples, n, d)
+
+
 class IPAdapter:
     def __init__(self, sd_pipe, image_encoder_path, ip_ckpt, device, num_tokens=4, target_blocks=None,
                  number_class_crossattention=None):
-        self.device = device
-        self.image_encoder_path = image_encoder_path
-        self.ip_ckpt = ip_ckpt
-        self.num_tokens = num_tokens
-        self.pipe = sd_pipe.to(self.device)
+        self.device, self.num_tokens = device, num_tokens
+        self.image_encoder_path, self.ip_ckpt = image_encoder_path, ip_ckpt
+        self.pipe = sd_pipe.to(device)
         self.set_ip_adapter()
 
         # image encoder (CLIP ViT-bigG/14 with projection for SDXL): a [3P] transformers model, "next" row f2
@@ -65,92 +97,75 @@ class IPAdapter:
         return self.pipe.unet.config.pooled_embed_dim
 
     def init_proj(self):
-        image_proj_model = ImageProjModel(
-            cross_attention_dim=self.pipe.unet.config.cross_attention_dim,
-            clip_embeddings_dim=self._clip_dim(),
-            clip_extra_context_tokens=self.num_tokens,
-        ).to(self.device, dtype=torch.float16)
-        return image_proj_model.requires_grad_(False)
+        proj = ImageProjModel(cross_attention_dim=self.pipe.unet.config.cross_attention_dim,
+                              clip_embeddings_dim=self._clip_dim(), clip_extra_context_tokens=self.num_tokens)
+        return proj.to(self.device, dtype=torch.float16).requires_grad_(False)
 
     # ---- reference :99-133 ------------------------------------------------------------------------------------------
     def set_ip_adapter(self):
-        unet = self.pipe.unet
-        attn_procs = {}
-        for name in unet.attn_processors.keys():
-            cross_attention_dim = None if name.endswith("attn1.processor") else unet.config.cross_attention_dim
-            if name.startswith("mid_block"):
-                hidden_size = unet.config.block_out_channels[-1]
-            elif name.startswith("up_blocks"):
-                block_id = int(name[len("up_blocks.")])
-                hidden_size = list(reversed(unet.config.block_out_channels))[block_id]
-            elif name.startswith("down_blocks"):
-                block_id = int(name[len("down_blocks.")])
-                hidden_size = unet.config.block_out_channels[block_id]
-            if cross_attention_dim is None:
-                attn_procs[name] = AttnProcessor()
-            else:
-                skip = "down_blocks.2.attentions.1" not in name                      # :117-123
-                with torch.device("meta"):
-                    proc = IPAttnProcessor(hidden_size=hidden_size, cross_attention_dim=cross_attention_dim,
-                                           num_tokens=self.num_tokens, skip=skip)
-                proc = proc.to_empty(device=self.device).to(torch.float16).requires_grad_(False)
-                for p in proc.parameters():
-                    p.zero_()
-                attn_procs[name] = proc
-        unet.set_attn_processor(attn_procs)
+        """One processor per attention module: plain for self-attention, decoupled image-prompt processors for the 70
+        cross-attention modules -- with the image branch switched on only inside IP_LAYER_MARKER."""
         if hasattr(self.pipe, "controlnet"):
             raise IHError("ControlNet pipelines are outside the SDXL IP-adapter hot path")
+        cfg = self.pipe.unet.config
+        table = {}
+        for name in self.pipe.unet.attn_processors:
+            if name.endswith("attn1.processor"):
+                table[name] = AttnProcessor()
+                continue
+            with torch.device("meta"):
+                proc = IPAttnProcessor(hidden_size=_block_channels(name, cfg.block_out_channels),
+                                       cross_attention_dim=cfg.cross_attention_dim, num_tokens=self.num_tokens,
+                                       skip=IP_LAYER_MARKER not in name)
+            proc = proc.to_empty(device=self.device).to(torch.float16).requires_grad_(False)
+            for prm in proc.parameters():
+                prm.zero_()                       # inert until load_ip_adapter fills to_k_ip / to_v_ip
+            table[name] = proc
+        self.pipe.unet.set_attn_processor(table)
 
     # ---- reference :135-154 -----------------------------------------------------------------------------------------
     def load_ip_adapter(self):
         if self.ip_ckpt is None:
             return   # random / zero-initialised adapter (benchmarks and tests: there are no checkpoints offline)
-        if os.path.splitext(self.ip_ckpt)[-1] == ".safetensors":
+        if str(self.ip_ckpt).endswith(".safetensors"):
             from safetensors import safe_open
-            state_dict = {"image_proj": {}, "ip_adapter": {}, "composed_adapter": {}}
-            with safe_open(self.ip_ckpt, framework="pt", device="cpu") as f:
-                for key in f.keys():
-                    for prefix, dst in (("image_proj.", "image_proj"), ("image_proj_model.", "image_proj"),
-                                        ("ip_adapter.", "ip_adapter"), ("adapter_modules.", "ip_adapter"),
-                                        ("composed_adapter.", "composed_adapter"),
-                                        ("composed_modules.", "composed_adapter")):
-                        if key.startswith(prefix):
-                            state_dict[dst][key[len(prefix):]] = f.get_tensor(key)
-                            break
+            parts = {"image_proj": {}, "ip_adapter": {}, "composed_adapter": {}}
+            with safe_open(self.ip_ckpt, framework="pt", device="cpu") as fh:
+                for key in fh.keys():
+                    hit = next(((pre, dst) for pre, dst in _CKPT_PREFIXES if key.startswith(pre)), None)
+                    if hit is not None:
+                        parts[hit[1]][key[len(hit[0]):]] = fh.get_tensor(key)
         else:
-            state_dict = torch.load(self.ip_ckpt, map_location="cpu")
-        self.image_proj_model.load_state_dict(state_dict["image_proj"])
-        if self.number_class_crossattention is not None and state_dict.get("composed_adapter"):
-            self.number_class_crossattention.load_state_dict(state_dict["composed_adapter"])
-        ip_layers = torch.nn.ModuleList(self.pipe.unet.attn_processors.values())
-        ip_layers.load_state_dict(state_dict["ip_adapter"])       # strict, index-keyed: all 70 attn2 own tensors (:153)
+            parts = torch.load(self.ip_ckpt, map_location="cpu")                   # the 3-key dict of convert_bin.py
+        self.image_proj_model.load_state_dict(parts["image_proj"])
+        if self.number_class_crossattention is not None and parts.get("composed_adapter"):
+            self.number_class_crossattention.load_state_dict(parts["composed_adapter"])
+        # strict and index-keyed: every one of the 70 cross-attention processors owns to_k_ip / to_v_ip (:153)
+        torch.nn.ModuleList(self.pipe.unet.attn_processors.values()).load_state_dict(parts["ip_adapter"])
         self.pipe.unet.finalize()
 
     # ---- reference :158-182 -----------------------------------------------------------------------------------------
     @torch.inference_mode()
     def get_image_embeds(self, pil_image=None, clip_image_embeds=None, extra_prompt_embeds=None):
-        if pil_image is not None:
+        """-> (conditional, unconditional) image-prompt tokens [n, num_tokens, cross_attention_dim]."""
+        if pil_image is None:
+            emb = clip_image_embeds
+        else:
             if self.image_encoder is None:
                 raise IHError("no CLIP image encoder loaded (image_encoder_path): pass clip_image_embeds=")
-            if isinstance(pil_image, Image.Image):
-                pil_image = [pil_image]
-            clip_image = self.clip_image_processor(images=pil_image, return_tensors="pt").pixel_values
-            clip_image_embeds = self.image_encoder(clip_image.to(self.device, dtype=torch.float16)).image_embeds
-        else:
-            clip_image_embeds = clip_image_embeds.to(self.device, dtype=torch.float16)
-        clip_image_embeds = clip_image_embeds.contiguous()
+            images = [pil_image] if isinstance(pil_image, Image.Image) else list(pil_image)
+            pixels = self.clip_image_processor(images=images, return_tensors="pt").pixel_values
+            emb = self.image_encoder(pixels.to(self.device, dtype=torch.float16)).image_embeds
+        emb = emb.to(self.device, dtype=torch.float16).contiguous()
         if extra_prompt_embeds is not None and self.number_class_crossattention is not None:      # :169-173
-            extra_prompt_embeds = extra_prompt_embeds.to(self.device, torch.float16)
-            clip_image_embeds = self.number_class_crossattention(extra_prompt_embeds, clip_image_embeds,
-                                                                 add_to=clip_image_embeds)
-        image_prompt_embeds = self.image_proj_model(clip_image_embeds)                            # :175
-        uncond_image_prompt_embeds = self.image_proj_model(torch.zeros_like(clip_image_embeds))  # :176
-        return image_prompt_embeds, uncond_image_prompt_embeds
+            aux = extra_prompt_embeds.to(self.device, torch.float16)
+            emb = self.number_class_crossattention(aux, emb, add_to=emb)      # harmony-aware residual on the embedding
+        return self.image_proj_model(emb), self.image_proj_model(torch.zeros_like(emb))           # :175-176
 
     def set_scale(self, scale):
-        for attn_processor in self.pipe.unet.attn_processors.values():
-            if isinstance(attn_processor, IPAttnProcessor):
-                attn_processor.scale = scale
+        for proc in self.pipe.unet.attn_processors.values():
+            if isinstance(proc, IPAttnProcessor):
+                proc.scale = scale
 
 
 class IPAdapterXL(IPAdapter):
@@ -166,47 +181,31 @@ class IPAdapterXL(IPAdapter):
                  seed=None, num_inference_steps=30, clip_image_embeds=None, **kwargs):
         """reference :257-340.  `clip_image_embeds=` is an extension for environments without the CLIP vision weights."""
         self.set_scale(scale)
-        if pil_image is not None:
-            num_prompts = 1 if isinstance(pil_image, Image.Image) else len(pil_image)
+        if pil_image is None:
+            n_img = clip_image_embeds.shape[0]
         else:
-            num_prompts = clip_image_embeds.shape[0]
-        if prompt is None:
-            prompt = "best quality, high quality"
-        if negative_prompt is None:
-            negative_prompt = "monochrome, lowres, bad anatomy, worst quality, low quality"
-        if not isinstance(prompt, List):
-            prompt = [prompt] * num_prompts
-        if not isinstance(negative_prompt, List):
-            negative_prompt = [negative_prompt] * num_prompts
+            n_img = 1 if isinstance(pil_image, Image.Image) else len(pil_image)
+        prompts = _per_image(prompt, DEFAULT_PROMPT, n_img)
+        negatives = _per_image(negative_prompt, DEFAULT_NEGATIVE_PROMPT, n_img)
+        cfg_args = dict(num_images_per_prompt=num_samples, do_classifier_free_guidance=True, negative_prompt=negatives)
 
-        extra_prompt_embeds = None
-        if extra_text is not None:                                                                # :285-297
-            extra_prompt_embeds, _, _, _ = self.pipe.encode_prompt(
-                extra_text, num_images_per_prompt=num_samples, do_classifier_free_guidance=True,
-                negative_prompt=negative_prompt)
-        image_prompt_embeds, uncond_image_prompt_embeds = self.get_image_embeds(
-            pil_image=pil_image, clip_image_embeds=clip_image_embeds, extra_prompt_embeds=extra_prompt_embeds)  # :300
+        aux_embeds = None
+        if extra_text is not None:                                                 # :285-297 (auxiliary count/class text)
+            aux_embeds = self.pipe.encode_prompt(extra_text, **cfg_args)[0]
+        cond, uncond = self.get_image_embeds(pil_image=pil_image, clip_image_embeds=clip_image_embeds,
+                                             extra_prompt_embeds=aux_embeds)                       # :300
+        cond, uncond = _repeat_for_samples(cond, num_samples), _repeat_for_samples(uncond, num_samples)
 
-        bs_embed, seq_len, _ = image_prompt_embeds.shape                                          # :302-306
-        image_prompt_embeds = image_prompt_embeds.repeat(1, num_samples, 1).view(bs_embed * num_samples, seq_len, -1)
-        uncond_image_prompt_embeds = uncond_image_prompt_embeds.repeat(1, num_samples, 1).view(
-            bs_embed * num_samples, seq_len, -1)
+        text, neg_text, pooled, neg_pooled = self.pipe.encode_prompt(prompts, **cfg_args)          # :308-319
+        prompt_embeds = torch.cat([text.to(cond.device), cond], dim=1)                             # :321 -> 77 + 4 tokens
+        negative_prompt_embeds = torch.cat([neg_text.to(cond.device), uncond], dim=1)              # :322
 
-        (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
-         negative_pooled_prompt_embeds) = self.pipe.encode_prompt(
-            prompt, num_images_per_prompt=num_samples, do_classifier_free_guidance=True,
-            negative_prompt=negative_prompt)                                                      # :308-319
-        dev = image_prompt_embeds.device
-        prompt_embeds = torch.cat([prompt_embeds.to(dev), image_prompt_embeds], dim=1)            # :321
-        negative_prompt_embeds = torch.cat([negative_prompt_embeds.to(dev), uncond_image_prompt_embeds], dim=1)  # :322
-
-        gen_device = "cpu" if isinstance(seed, list) else self.device
-        self.generator = get_generator(seed, gen_device)                                          # :328
-        images = self.pipe(prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
-                           pooled_prompt_embeds=pooled_prompt_embeds,
-                           negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
-                           num_inference_steps=num_inference_steps, generator=self.generator, **kwargs).images
-        return images
+        # a list of seeds means one CPU generator per image, so a candidate noise does not depend on its batch slot
+        self.generator = get_generator(seed, "cpu" if isinstance(seed, list) else self.device)     # :328
+        result = self.pipe(prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+                           pooled_prompt_embeds=pooled, negative_pooled_prompt_embeds=neg_pooled,
+                           num_inference_steps=num_inference_steps, generator=self.generator, **kwargs)
+        return result.images
 
 
 class IPAdapterPlusXL(IPAdapter):
@@ -214,55 +213,40 @@ class IPAdapterPlusXL(IPAdapter):
     states."""
 
     def init_proj(self):
-        emb = self.image_encoder.config.hidden_size if self.image_encoder is not None else 1664
-        image_proj_model = Resampler(dim=1280, depth=4, dim_head=64, heads=20, num_queries=self.num_tokens,
-                                     embedding_dim=emb, output_dim=self.pipe.unet.config.cross_attention_dim,
-                                     ff_mult=4).to(self.device, dtype=torch.float16)
-        return image_proj_model.requires_grad_(False)
+        width = self.image_encoder.config.hidden_size if self.image_encoder is not None else 1664   # ViT-bigG
+        resampler = Resampler(dim=1280, depth=4, dim_head=64, heads=20, num_queries=self.num_tokens, embedding_dim=width,
+                              output_dim=self.pipe.unet.config.cross_attention_dim, ff_mult=4)
+        return resampler.to(self.device, dtype=torch.float16).requires_grad_(False)
 
     @torch.inference_mode()
     def get_image_embeds(self, pil_image=None, clip_hidden_states=None, uncond_clip_hidden_states=None):
+        """Resampler tokens of the penultimate CLIP hidden states; the unconditional branch encodes a black image."""
         if pil_image is not None:
             if self.image_encoder is None:
                 raise IHError("no CLIP image encoder loaded: pass clip_hidden_states= / uncond_clip_hidden_states=")
-            if isinstance(pil_image, Image.Image):
-                pil_image = [pil_image]
-            clip_image = self.clip_image_processor(images=pil_image, return_tensors="pt").pixel_values
-            clip_image = clip_image.to(self.device, dtype=torch.float16)
-            clip_hidden_states = self.image_encoder(clip_image, output_hidden_states=True).hidden_states[-2]
-            uncond_clip_hidden_states = self.image_encoder(torch.zeros_like(clip_image),
-                                                           output_hidden_states=True).hidden_states[-2]
-        image_prompt_embeds = self.image_proj_model(clip_hidden_states.to(self.device, torch.float16))
-        uncond_image_prompt_embeds = self.image_proj_model(uncond_clip_hidden_states.to(self.device, torch.float16))
-        return image_prompt_embeds, uncond_image_prompt_embeds
+            images = [pil_image] if isinstance(pil_image, Image.Image) else list(pil_image)
+            pixels = self.clip_image_processor(images=images, return_tensors="pt").pixel_values
+            pixels = pixels.to(self.device, dtype=torch.float16)
+
+            def penultimate(x):
+                return self.image_encoder(x, output_hidden_states=True).hidden_states[-2]
+            clip_hidden_states, uncond_clip_hidden_states = penultimate(pixels), penultimate(torch.zeros_like(pixels))
+        to_dev = lambda t: t.to(self.device, torch.float16)  # noqa: E731
+        return self.image_proj_model(to_dev(clip_hidden_states)), self.image_proj_model(to_dev(uncond_clip_hidden_states))
 
     def generate(self, pil_image=None, prompt=None, negative_prompt=None, scale=1.0, num_samples=4, seed=None,
                  num_inference_steps=30, clip_hidden_states=None, uncond_clip_hidden_states=None, **kwargs):
+        """reference :423-478 (no auxiliary text / HarmonyAttention on this variant)."""
         self.set_scale(scale)
-        num_prompts = 1 if (pil_image is None or isinstance(pil_image, Image.Image)) else len(pil_image)
-        if prompt is None:
-            prompt = "best quality, high quality"
-        if negative_prompt is None:
-            negative_prompt = "monochrome, lowres, bad anatomy, worst quality, low quality"
-        if not isinstance(prompt, List):
-            prompt = [prompt] * num_prompts
-        if not isinstance(negative_prompt, List):
-            negative_prompt = [negative_prompt] * num_prompts
-        image_prompt_embeds, uncond_image_prompt_embeds = self.get_image_embeds(
-            pil_image, clip_hidden_states, uncond_clip_hidden_states)
-        bs_embed, seq_len, _ = image_prompt_embeds.shape
-        image_prompt_embeds = image_prompt_embeds.repeat(1, num_samples, 1).view(bs_embed * num_samples, seq_len, -1)
-        uncond_image_prompt_embeds = uncond_image_prompt_embeds.repeat(1, num_samples, 1).view(
-            bs_embed * num_samples, seq_len, -1)
-        (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
-         negative_pooled_prompt_embeds) = self.pipe.encode_prompt(
-            prompt, num_images_per_prompt=num_samples, do_classifier_free_guidance=True,
-            negative_prompt=negative_prompt)
-        dev = image_prompt_embeds.device
-        prompt_embeds = torch.cat([prompt_embeds.to(dev), image_prompt_embeds], dim=1)
-        negative_prompt_embeds = torch.cat([negative_prompt_embeds.to(dev), uncond_image_prompt_embeds], dim=1)
+        n_img = 1 if (pil_image is None or isinstance(pil_image, Image.Image)) else len(pil_image)
+        prompts = _per_image(prompt, DEFAULT_PROMPT, n_img)
+        negatives = _per_image(negative_prompt, DEFAULT_NEGATIVE_PROMPT, n_img)
+        cond, uncond = self.get_image_embeds(pil_image, clip_hidden_states, uncond_clip_hidden_states)
+        cond, uncond = _repeat_for_samples(cond, num_samples), _repeat_for_samples(uncond, num_samples)
+        text, neg_text, pooled, neg_pooled = self.pipe.encode_prompt(
+            prompts, num_images_per_prompt=num_samples, do_classifier_free_guidance=True, negative_prompt=negatives)
         generator = get_generator(seed, "cpu" if isinstance(seed, list) else self.device)
-        return self.pipe(prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
-                         pooled_prompt_embeds=pooled_prompt_embeds,
-                         negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
+        return self.pipe(prompt_embeds=torch.cat([text.to(cond.device), cond], dim=1),
+                         negative_prompt_embeds=torch.cat([neg_text.to(cond.device), uncond], dim=1),
+                         pooled_prompt_embeds=pooled, negative_pooled_prompt_embeds=neg_pooled,
                          num_inference_steps=num_inference_steps, generator=generator, **kwargs).images

@@ -11,11 +11,8 @@ def is_torch2_available():
 def get_generator(seed, device):
     """seed -> torch.Generator; a list of seeds -> a list of generators, one per image (utils.py:83-93).  One generator
     per image is what makes a PNS candidate noise identical on whichever rank / batch slot it lands."""
-    if seed is not None:
-        if isinstance(seed, list):
-            generator = [torch.Generator(device).manual_seed(seed_item) for seed_item in seed]
-        else:
-            generator = torch.Generator(device).manual_seed(seed)
-    else:
-        generator = None
-    return generator
+    def make(value):
+        return torch.Generator(device).manual_seed(value)
+    if seed is None:
+        return None
+    return [make(v) for v in seed] if isinstance(seed, list) else make(seed)

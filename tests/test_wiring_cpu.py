@@ -199,3 +199,22 @@ def test_ip_adapter_xl_generate_call_surface(patched, tmp_path):
     assert isinstance(pil, list) and len(pil) == 2 and pil[0].size == (128, 128) and pil[0].mode == "RGB"
     ip_model.set_scale(0.25)
     assert all(p.scale == 0.25 for p in pipe.unet.attn_processors.values() if hasattr(p, "to_k_ip"))
+
+
+def test_ip_adapter_plus_xl_generate_call_surface(patched):
+    """IPAdapterPlusXL (reference :389-478): Resampler tokens (16) from penultimate CLIP hidden states appended to the 77
+    text tokens, list-of-seeds generators, latent output."""
+    from imagharmony_b200.config import TINY
+    from ip_adapter import IPAdapterPlusXL
+    from ip_adapter.custom_pipelines import StableDiffusionXLCustomPipeline
+    pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu")
+    model = IPAdapterPlusXL(pipe, None, None, "cpu", num_tokens=16)
+    assert sum(1 for p in pipe.unet.attn_processors.values() if hasattr(p, "to_k_ip")) == \
+        sum(1 for n in pipe.unet.attn_processors if n.endswith("attn2.processor"))
+    g = torch.Generator().manual_seed(0)
+    hs, un = torch.randn(1, 257, 1664, generator=g).half(), torch.randn(1, 257, 1664, generator=g).half()
+    cond, uncond = model.get_image_embeds(None, hs, un)
+    assert cond.shape == uncond.shape == (1, 16, TINY.cross_attention_dim)
+    out = model.generate(prompt="lions", num_samples=2, num_inference_steps=1, seed=[1, 2], clip_hidden_states=hs,
+                         uncond_clip_hidden_states=un, output_type="latent", height=128, width=128)
+    assert out.shape == (2, 4, 16, 16) and torch.isfinite(out.float()).all()
