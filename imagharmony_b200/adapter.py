@@ -88,8 +88,13 @@ class HarmonyAttention(nn.Module):
         B = image_embeds.shape[0]
         x = ops.linear_small(image_embeds.contiguous(), self.fc1.weight, self.fc1.bias)             # :254
         x = x.reshape(B, self.reshape_blocks, self.cross_query_dim)                                 # :255
-        # one copy of the auxiliary text is enough: repeated keys do not change a softmax-weighted mean (C.11)
-        attended = self.fusion_text_image(x, text_embeds[:B] if text_embeds.shape[0] >= B else text_embeds)
+        # encode_prompt(extra_text, num_images_per_prompt=n) lays the rows out [a,a,..,b,b,..]; the reference's
+        # Cross_Attention folds each image's n copies into its key axis (view(B, -1, D), attention_processor.py:37-41).
+        # Repeated keys do not change a softmax-weighted mean (C.11), so ONE copy per image group is taken instead.
+        rows = text_embeds.shape[0]
+        if rows % B != 0:
+            raise IHError(f"HarmonyAttention: {rows} auxiliary-text rows cannot be grouped over {B} image embeddings")
+        attended = self.fusion_text_image(x, text_embeds[:: rows // B].contiguous())
         a = ops.layernorm(attended.reshape(B, -1), self.ln.weight, self.ln.bias, self.ln.eps)       # :262-263
         return ops.linear_small(a, self.fc2.weight, self.fc2.bias, out_scale=float(self.scale), addend=add_to)  # :264
 

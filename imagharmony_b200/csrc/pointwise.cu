@@ -263,6 +263,94 @@ __global__ void euler_cfg_kernel(const __half* __restrict__ noise, __half* __res
     model_in[total + idx] = mi;
   }
 }
+// General form of the step (custom_pipelines.py:346-357): classifier-free guidance on or off (:223,332,348) and the
+// optional guidance rescale of :352-354 ([3P] diffusers rescale_noise_cfg: per-image unbiased std of the text branch
+// and of the guided prediction over all non-batch elements, fp16 tensors -> fp16 rounding points).  ONE block per
+// image: a first sweep forms the guided prediction and its statistics (double accumulators, fixed reduction order:
+// deterministic), a second sweep -- the image is L1/L2 resident -- applies rescale + Euler.  n_images blocks of
+// 1024 threads; a 4 x 128 x 128 latent is 64 elements per thread.
+__global__ void __launch_bounds__(1024) euler_ex_kernel(const __half* __restrict__ noise, __half* __restrict__ latents,
+                                                         __half* __restrict__ model_in,
+                                                         const float* __restrict__ sigmas, const int* __restrict__ step,
+                                                         float guidance, float rescale, long long per_image,
+                                                         int n_images, int cfg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int img = blockIdx.x;
+  const int i = *step;
+  const float sigma = sigmas[i], sigma_next = sigmas[i + 1];
+  const float den_next = sqrtf(sigma_next * sigma_next + 1.f);
+  const long long total = per_image * n_images;
+  const long long base = (long long)img * per_image;
+  auto guided = [&](long long idx, float& c_out) -> float {
+    if (!cfg) {
+      c_out = __half2float(noise[idx]);
+      return c_out;
+    }
+    const float u = __half2float(noise[idx]);
+    const float c = __half2float(noise[total + idx]);
+    c_out = c;
+    const float d1 = __half2float(__float2half_rn(c - u));
+    const float d2 = __half2float(__float2half_rn(guidance * d1));
+    return __half2float(__float2half_rn(u + d2));
+  };
+  float factor = 1.f;   // fp16(std_text / std_cfg)
+  if (cfg && rescale > 0.f) {
+    double s_t = 0.0, q_t = 0.0, s_g = 0.0, q_g = 0.0;
+    for (long long e = threadIdx.x; e < per_image; e += blockDim.x) {
+      float c;
+      const float g = guided(base + e, c);
+      s_t += c;
+      q_t += (double)c * c;
+      s_g += g;
+      q_g += (double)g * g;
+    }
+    __shared__ double red[4][32];
+    __shared__ float s_factor;
+    double v[4] = {s_t, q_t, s_g, q_g};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t[4] = {0, 0, 0, 0};
+      const int nw = (blockDim.x + 31) >> 5;
+      for (int k = 0; k < 4; ++k)
+        for (int w = 0; w < nw; ++w) t[k] += red[k][w];
+      const double n = (double)per_image;
+      const double var_t = fmax((t[1] - t[0] * t[0] / n) / (n - 1.0), 0.0);
+      const double var_g = fmax((t[3] - t[2] * t[2] / n) / (n - 1.0), 0.0);
+      const float std_t = __half2float(__float2half_rn((float)sqrt(var_t)));   // torch.std of an fp16 tensor -> fp16
+      const float std_g = __half2float(__float2half_rn((float)sqrt(var_g)));
+      s_factor = __half2float(__float2half_rn(std_t / std_g));
+    }
+    __syncthreads();
+    factor = s_factor;
+  }
+  for (long long e = threadIdx.x; e < per_image; e += blockDim.x) {
+    const long long idx = base + e;
+    float c;
+    float eps = guided(idx, c);
+    if (cfg && rescale > 0.f) {
+      const float resc = __half2float(__float2half_rn(eps * factor));                  // noise_cfg * (std_text / std_cfg)
+      const float a = __half2float(__float2half_rn(rescale * resc));
+      const float b = __half2float(__float2half_rn((1.f - rescale) * eps));
+      eps = __half2float(__float2half_rn(a + b));
+    }
+    const float x = __half2float(latents[idx]);
+    const float x0 = x - __half2float(__float2half_rn(sigma * eps));
+    const float deriv = (x - x0) / sigma;
+    const float xn = x + deriv * (sigma_next - sigma);
+    const __half xh = __float2half_rn(xn);
+    latents[idx] = xh;
+    const __half mi = __float2half_rn(__half2float(xh) / den_next);
+    model_in[idx] = mi;
+    if (cfg) model_in[total + idx] = mi;
+  }
+}
+
 __global__ void step_inc_kernel(int* step) {
   pdl_launch_dependents();
   pdl_wait();
@@ -271,7 +359,7 @@ __global__ void step_inc_kernel(int* step) {
 
 __global__ void scale_model_input_kernel(const __half* __restrict__ latents, __half* __restrict__ model_in,
                                          const float* __restrict__ sigmas, const int* __restrict__ step,
-                                         long long total) {
+                                         long long total, int duplicate) {
   pdl_launch_dependents();
   pdl_wait();
   const float sigma = sigmas[*step];
@@ -280,7 +368,7 @@ __global__ void scale_model_input_kernel(const __half* __restrict__ latents, __h
        idx += (long long)gridDim.x * blockDim.x) {
     const __half mi = __float2half_rn(__half2float(latents[idx]) / den);
     model_in[idx] = mi;
-    model_in[total + idx] = mi;
+    if (duplicate) model_in[total + idx] = mi;   // CFG batch [uncond | cond] (custom_pipelines.py:332)
   }
 }
 
@@ -589,11 +677,30 @@ extern "C" int ih_euler_cfg_step(const void* noise_pred, void* latents, void* mo
   return 0;
 }
 
+extern "C" int ih_euler_step_ex(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
+                                float guidance, float guidance_rescale, long long n_per_image, int n_images,
+                                int use_cfg, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  IH_CHECK(noise_pred && latents && model_in && sigmas && step, IH_ERR_ARG, "ih_euler_step_ex: null pointer");
+  IH_CHECK(n_per_image > 1 && n_images > 0, IH_ERR_SHAPE, "ih_euler_step_ex: bad shape");
+  IH_CHECK(guidance_rescale >= 0.f && guidance_rescale <= 1.f, IH_ERR_ARG, "ih_euler_step_ex: guidance_rescale outside [0, 1]");
+  IH_CUDA(launch_kernel(euler_ex_kernel, dim3(n_images), dim3(1024), (size_t)(0), stream, (const __half*)noise_pred,
+                        (__half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, guidance,
+                        guidance_rescale, n_per_image, n_images, use_cfg ? 1 : 0));
+  IH_CUDA(launch_kernel(step_inc_kernel, dim3(1), dim3(1), (size_t)(0), stream, (int*)step));
+  return 0;
+}
+
 extern "C" int ih_scale_model_input(const void* latents, void* model_in, const void* sigmas, const void* step,
                                     long long total, void* stream) {
+  return ih_scale_model_input_ex(latents, model_in, sigmas, step, total, 1, stream);
+}
+
+extern "C" int ih_scale_model_input_ex(const void* latents, void* model_in, const void* sigmas, const void* step,
+                                       long long total, int duplicate, void* stream) {
   IH_CHECK(latents && model_in && sigmas && step, IH_ERR_ARG, "ih_scale_model_input: null pointer");
   IH_CUDA(launch_kernel(scale_model_input_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
-      (const __half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, total));
+      (const __half*)latents, (__half*)model_in, (const float*)sigmas, (const int*)step, total, duplicate ? 1 : 0));
   return 0;
 }
 

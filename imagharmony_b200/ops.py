@@ -138,18 +138,34 @@ def pack_conv3x3_weight(w_oihw: torch.Tensor) -> torch.Tensor:
 
 
 _attn_ws = {}
+_ws_generation = 0
+
+
+def workspace_generation() -> int:
+    """Bumped whenever a persistent scratch buffer (attention KV-split parts, GroupNorm statistics) is re-allocated.
+    A CUDA graph captured under an older generation may hold a pointer to freed memory: DenoiseEngine compares this
+    number with the one it recorded at capture time and re-captures instead of replaying a stale graph."""
+    return _ws_generation
+
+
+def _bump_generation() -> None:
+    global _ws_generation
+    _ws_generation += 1
 
 
 def _attn_workspace(device, need: int) -> Optional[torch.Tensor]:
-    """Persistent scratch for the KV-split self-attention parts (one per device; calls are stream-ordered)."""
+    """Persistent grow-only scratch for the KV-split self-attention parts (one per device; calls are stream-ordered)."""
     if need <= 0:
         return None
     ws = _attn_ws.get(device)
     if ws is None or ws.numel() < need:
         if torch.cuda.is_current_stream_capturing():
             raise IHError("attention workspace must be created before CUDA-graph capture (run one warm-up step)")
+        had = ws is not None
         ws = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=device)
         _attn_ws[device] = ws
+        if had:
+            _bump_generation()
     return ws
 
 
@@ -218,8 +234,11 @@ def _gn_workspace(device, B: int, groups: int) -> torch.Tensor:
     if ws is None or ws.numel() < need:
         if torch.cuda.is_current_stream_capturing():
             raise IHError("groupnorm workspace must be created before CUDA-graph capture (run one warm-up step)")
+        had = ws is not None
         ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
         _gn_ws[device] = ws
+        if had:
+            _bump_generation()
     return ws
 
 
@@ -420,8 +439,31 @@ def euler_cfg_step(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: to
                                 step.data_ptr(), float(guidance), per, n, _stream()), "ih_euler_cfg_step")
 
 
-def scale_model_input(latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor, step: torch.Tensor) -> None:
+def euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor,
+               step: torch.Tensor, guidance: float, *, use_cfg: bool = True, guidance_rescale: float = 0.0) -> None:
+    """One scheduler transition with the reference's loop options: the default (CFG, no rescale) is the fused
+    grid-stride kernel `ih_euler_cfg_step`; guidance_scale <= 1 and guidance_rescale > 0 (custom_pipelines.py:223,
+    :352-354) run `ih_euler_step_ex` (one block per image, per-image std for the rescale)."""
+    if use_cfg and not guidance_rescale:
+        return euler_cfg_step(noise_pred, latents, model_in, sigmas, step, guidance)
+    lib = _lib.load()
+    _req(noise_pred, "noise_pred"); _req(latents, "latents"); _req(model_in, "model_in")
+    _req(sigmas, "sigmas", torch.float32); _req(step, "step", torch.int32)
+    n = latents.shape[0]
+    per = latents.numel() // n
+    want = (2 * n if use_cfg else n) * per
+    if noise_pred.numel() != want or model_in.numel() != want:
+        raise IHError(f"euler_step: noise_pred / model_in must hold {want} elements (use_cfg={use_cfg})")
+    check(lib.ih_euler_step_ex(noise_pred.data_ptr(), latents.data_ptr(), model_in.data_ptr(), sigmas.data_ptr(),
+                               step.data_ptr(), float(guidance), float(guidance_rescale), per, n, int(use_cfg),
+                               _stream()), "ih_euler_step_ex")
+
+
+def scale_model_input(latents: torch.Tensor, model_in: torch.Tensor, sigmas: torch.Tensor, step: torch.Tensor,
+                      duplicate: bool = True) -> None:
     lib = _lib.load()
     _req(latents, "latents"); _req(model_in, "model_in")
-    check(lib.ih_scale_model_input(latents.data_ptr(), model_in.data_ptr(), sigmas.data_ptr(), step.data_ptr(),
-                                   latents.numel(), _stream()), "ih_scale_model_input")
+    if model_in.numel() != (2 if duplicate else 1) * latents.numel():
+        raise IHError("scale_model_input: model_in must hold the CFG pair (duplicate=True) or one copy of the latents")
+    check(lib.ih_scale_model_input_ex(latents.data_ptr(), model_in.data_ptr(), sigmas.data_ptr(), step.data_ptr(),
+                                      latents.numel(), int(duplicate), _stream()), "ih_scale_model_input_ex")

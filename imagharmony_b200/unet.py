@@ -322,8 +322,10 @@ class UNet2DConditionModel(nn.Module):
         self.conv_out = nn.Conv2d(boc[0], cfg.out_channels, 3, padding=1)
         self._w_temb = None
         self._b_temb = None
-        self._aug = None          # (key, aug_emb [B, time_embed_dim])
+        self._aug = None          # (key, aug_emb [B, time_embed_dim]) of the last prepare_conditioning()
+        self._aug_bufs = {}       # B -> buffer; kept for the life of the model: captured CUDA graphs point at them
         self._text_only = None
+        self.graph_epoch = 0      # bumped when weights / processors change: graphs captured earlier are stale
 
     # ------------------------------------------------------------------------------------------------------------
     @classmethod
@@ -371,6 +373,7 @@ class UNet2DConditionModel(nn.Module):
     def set_attn_processor(self, procs) -> None:
         for name, m in self._attn_modules():
             m.processor = procs[f"{name}.processor"] if isinstance(procs, dict) else procs
+        self.graph_epoch += 1
 
     def finalize(self):
         """Derive kernel-layout weights. Call after (re)loading parameters."""
@@ -409,6 +412,7 @@ class UNet2DConditionModel(nn.Module):
         for p in self.attn_processors.values():
             if hasattr(p, "invalidate"):
                 p.invalidate()
+        self.graph_epoch += 1
 
     # ------------------------------------------------------------------------------------------------------------
     def prepare_conditioning(self, encoder_hidden_states: torch.Tensor, text_embeds: torch.Tensor,
@@ -429,9 +433,21 @@ class UNet2DConditionModel(nn.Module):
         tid = ops.sinusoid(time_ids.reshape(-1).float().contiguous(), cfg.addition_time_embed_dim, B * 6)
         add_in = torch.cat([text_embeds.to(torch.float16), tid.reshape(B, -1)], dim=-1).contiguous()
         h = ops.linear_small(add_in, self.add_embedding.linear_1.weight, self.add_embedding.linear_1.bias, act_out=True)
-        prev = self._aug[1] if (self._aug is not None and self._aug[1].shape[0] == B) else None   # keep the address
-        aug = ops.linear_small(h, self.add_embedding.linear_2.weight, self.add_embedding.linear_2.bias, out=prev)
-        self._aug = ((text_embeds.data_ptr(), time_ids.data_ptr(), B), aug)
+        buf = self._aug_bufs.get(B)                            # one buffer per batch size, never freed or moved
+        if buf is None or buf.device != h.device:
+            buf = torch.empty((B, cfg.time_embed_dim), dtype=torch.float16, device=h.device)
+            self._aug_bufs[B] = buf
+        aug = ops.linear_small(h, self.add_embedding.linear_2.weight, self.add_embedding.linear_2.bias, out=buf)
+        self._aug = (self._aug_key(text_embeds, time_ids, B), aug)
+
+    @staticmethod
+    def _aug_key(text_embeds: torch.Tensor, time_ids: torch.Tensor, B: int):
+        def ver(t):
+            try:
+                return t._version
+            except RuntimeError:       # inference tensors do not track versions
+                return -1
+        return (text_embeds.data_ptr(), ver(text_embeds), time_ids.data_ptr(), ver(time_ids), B)
 
     def time_embeddings(self, timesteps: torch.Tensor, step: Optional[torch.Tensor], B: int) -> torch.Tensor:
         """-> temb_all [B, sum(Cout)]: every ResBlock's time_emb_proj(silu(emb)) in one launch."""
@@ -450,7 +466,7 @@ class UNet2DConditionModel(nn.Module):
         if self._w_temb is None:
             raise IHError("UNet2DConditionModel.finalize() has not been called")
         B = sample.shape[0]
-        key = None if text_embeds is None else (text_embeds.data_ptr(), time_ids.data_ptr(), B)
+        key = None if text_embeds is None else self._aug_key(text_embeds, time_ids, B)
         if self._aug is None or (key is not None and self._aug[0] != key):
             if text_embeds is None:
                 raise IHError("forward() needs text_embeds/time_ids (or a prior prepare_conditioning())")

@@ -170,9 +170,22 @@ int ih_nhwc_to_nchw_f16(const void* x, long long ldc, void* out, int B, long lon
 int ih_euler_cfg_step(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
                       float guidance, long long n_per_image, int n_images, void* stream);
 
+/* General scheduler transition: the loop options the reference accepts beyond the default CFG path.
+ *   use_cfg = 0 : guidance_scale <= 1 (custom_pipelines.py:223 do_classifier_free_guidance False): noise_pred and
+ *                 model_in are [n,4,H,W]; eps = noise_pred (:332,:348 skipped).
+ *   guidance_rescale > 0 (:352-354, [3P] diffusers rescale_noise_cfg): eps <- r * eps * (std(c) / std(eps)) + (1 - r) * eps
+ *                 with the per-image unbiased std over all non-batch elements, fp16 rounding points of the fp16 tensors.
+ * Otherwise identical to ih_euler_cfg_step (which stays the fast path for the default call). */
+int ih_euler_step_ex(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
+                     float guidance, float guidance_rescale, long long n_per_image, int n_images, int use_cfg,
+                     void* stream);
+
 /* model_in = cat([latents, latents]) / sqrt(sigma[*step]^2 + 1)   (custom_pipelines.py:332-334, first step). */
 int ih_scale_model_input(const void* latents, void* model_in, const void* sigmas, const void* step, long long total,
                          void* stream);
+/* same with duplicate = 0: model_in = latents / sqrt(...) for the no-CFG loop (custom_pipelines.py:332 else-branch). */
+int ih_scale_model_input_ex(const void* latents, void* model_in, const void* sigmas, const void* step, long long total,
+                            int duplicate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -111,7 +111,8 @@ class IPAttnProcessor2_0(torch.nn.Module):
         self.to_k_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
         self.to_v_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
         self.keep_attn_map = False     # the reference's attn_map side effect (:443-444) has no consumer: opt-in
-        self._kv = None                # (key, kv tensor [B*Nk, 2C], Nk, n_ip)
+        self._kv = None                # (key, kv tensor [B*Nk, 2C], Nk, n_ip) of the last prepare()
+        self._kv_bufs = {}             # (rows, 2C) -> buffer; kept until invalidate(): captured CUDA graphs point at them
         self._w_kv_ip = None
 
     # -- step-invariant K/V -------------------------------------------------------------------------------------
@@ -123,12 +124,28 @@ class IPAttnProcessor2_0(torch.nn.Module):
         return w
 
     def invalidate(self):
+        """Drop the cached K/V (weights changed).  Graphs captured against the old buffers are stale afterwards: the
+        owner (UNet2DConditionModel.finalize / set_attn_processor) bumps its graph epoch so DenoiseEngine re-captures."""
         self._kv = None
+        self._kv_bufs = {}
         self._w_kv_ip = None
+
+    def _kv_buffer(self, rows: int, cols: int, like: torch.Tensor) -> torch.Tensor:
+        """One K/V buffer per shape, never freed or moved while graphs may reference it (n=1 -> n=4 -> n=1 sequences of
+        two-phase PNS / generate(num_samples=...) replay each shape's graph against that shape's own buffer)."""
+        buf = self._kv_bufs.get((rows, cols))
+        if buf is None or buf.device != like.device:
+            buf = torch.empty((rows, cols), dtype=torch.float16, device=like.device)
+            self._kv_bufs[(rows, cols)] = buf
+        return buf
 
     @staticmethod
     def _key(ehs: torch.Tensor):
-        return (ehs.data_ptr(), tuple(ehs.shape), ehs._version)
+        try:
+            version = ehs._version
+        except RuntimeError:           # inference tensors do not track versions
+            version = -1
+        return (ehs.data_ptr(), tuple(ehs.shape), version)
 
     def prepare(self, attn, encoder_hidden_states: torch.Tensor, text_only: Optional[torch.Tensor] = None):
         """Compute and cache K/V for these encoder tokens: [text ; ip] for active layers, text only when skip."""
@@ -137,18 +154,14 @@ class IPAttnProcessor2_0(torch.nn.Module):
         n_text = L - self.num_tokens                                             # :402
         C = self.hidden_size
         w_kv = attn.fused_kv_weight()
-        prev = self._kv[1] if self._kv is not None else None   # reuse the buffer: captured CUDA graphs point at it
         if self.skip:
             if text_only is None:
                 text_only = ehs[:, :n_text].contiguous()
-            if prev is not None and prev.shape != (B * n_text, 2 * C):
-                prev = None
-            kv = ops.linear(text_only.reshape(B * n_text, D), w_kv, out=prev)    # :410-411
+            kv = ops.linear(text_only.reshape(B * n_text, D), w_kv,
+                            out=self._kv_buffer(B * n_text, 2 * C, ehs))         # :410-411
             self._kv = (self._key(ehs), kv, n_text, 0)
         else:
-            if prev is not None and prev.shape != (B * L, 2 * C):
-                prev = None
-            kv = ops.linear(ehs.reshape(B * L, D), w_kv, out=prev)               # text rows: to_k / to_v
+            kv = ops.linear(ehs.reshape(B * L, D), w_kv, out=self._kv_buffer(B * L, 2 * C, ehs))   # text rows: to_k / to_v
             ip = ehs[:, n_text:].contiguous().reshape(B * self.num_tokens, D)
             kv_ip = ops.linear(ip, self._ip_weight())                            # :432-433 to_k_ip / to_v_ip
             kv.view(B, L, 2 * C)[:, n_text:] = kv_ip.view(B, self.num_tokens, 2 * C)

@@ -117,7 +117,14 @@ class StableDiffusionXLCustomPipeline:
         return cls(unet, prompt_encoder=enc, vae=vae)
 
     def to(self, device=None, *args, **kwargs):
-        return self      # weights already live on the device the UNet was built on
+        """Weights live on the device the UNet was built on (from_random / from_pretrained take `device=`); moving 5 GB
+        of kernel-layout weights behind the caller's back is not offered, a mismatching request raises."""
+        if device is not None and not isinstance(device, torch.dtype):
+            want = torch.device(device)
+            have = torch.device(self.device)
+            if want.type != have.type or (want.index is not None and have.index is not None and want.index != have.index):
+                raise IHError(f"pipeline was built on {have}; build it with device={want!s} instead of .to({want!s})")
+        return self
 
     def enable_vae_tiling(self):  # test.py:73
         if self.vae is not None:
@@ -131,8 +138,9 @@ class StableDiffusionXLCustomPipeline:
 
     @property
     def engine(self) -> DenoiseEngine:
-        if self._engine is None:
-            self._engine = DenoiseEngine(self.unet)
+        if self._engine is None or self._engine.scheduler is not self.scheduler:
+            # the loop integrates the SAME scheduler object whose init_noise_sigma scaled the initial latents
+            self._engine = DenoiseEngine(self.unet, scheduler=self.scheduler)
         return self._engine
 
     @torch.no_grad()
@@ -191,35 +199,48 @@ class StableDiffusionXLCustomPipeline:
                  control_guidance_start: float = 0.0, control_guidance_end: float = 1.0, **ignored):
         """Parameter list of custom_pipelines.py:23-56.  Unknown keyword arguments are accepted and ignored, because
         IPAdapterXL.generate forwards a stray `number_class_crossattention=` into this call (test.py:38, demo.py:124)."""
-        if guidance_rescale and guidance_rescale > 0.0:
-            raise IHError("guidance_rescale > 0 is not implemented on the native path")
-        if denoising_end is not None or callback is not None:
-            raise IHError("denoising_end / callback are not supported inside the graph-replayed loop")
         height = height or self.default_sample_size * self.vae_scale_factor           # :189-190
         width = width or self.default_sample_size * self.vae_scale_factor
         original_size = original_size or (height, width)                              # :192-193
         target_size = target_size or (height, width)
-        if guidance_scale <= 1.0:
-            raise IHError("the native loop implements the classifier-free-guidance path (guidance_scale > 1)")
+        if callback is not None and (not isinstance(callback_steps, int) or callback_steps <= 0):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps}")   # [3P] check_inputs
+        do_classifier_free_guidance = guidance_scale > 1.0                            # :223
         (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds) = \
-            self.encode_prompt(prompt, prompt_2, None, num_images_per_prompt, True, negative_prompt, negative_prompt_2,
-                               prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
-                               negative_pooled_prompt_embeds)                        # :229-247
+            self.encode_prompt(prompt, prompt_2, None, num_images_per_prompt, do_classifier_free_guidance,
+                               negative_prompt, negative_prompt_2, prompt_embeds, negative_prompt_embeds,
+                               pooled_prompt_embeds, negative_pooled_prompt_embeds)  # :229-247
         batch = prompt_embeds.shape[0]
         self.scheduler.set_timesteps(num_inference_steps)                             # :250
         lat = self.prepare_latents(batch, self.unet.config.in_channels, height, width, torch.float16, self.device,
                                    generator, latents)                               # :255-265
-        add_time_ids = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)],
-                                    dtype=torch.float32).repeat(batch, 1)             # :277-284
+
+        def time_ids(size, crop, target):                                             # :277-284 _get_add_time_ids [3P]
+            return torch.tensor([list(size) + list(crop) + list(target)], dtype=torch.float32).repeat(batch, 1)
+        add_time_ids = time_ids(original_size, crops_coords_top_left, target_size)
+        negative_add_time_ids = None
+        if negative_original_size is not None and negative_target_size is not None:   # :285-294
+            negative_add_time_ids = time_ids(negative_original_size, negative_crops_coords_top_left, negative_target_size)
+        loop_steps = num_inference_steps
+        if denoising_end is not None and isinstance(denoising_end, float) and 0 < denoising_end < 1:   # :307-316
+            n_train = self.scheduler.num_train_timesteps
+            cutoff = int(round(n_train - denoising_end * n_train))
+            loop_steps = int(sum(1 for t in self.scheduler.timesteps if t >= cutoff))
         conditioning_scale = 1.0
         for attn_processor in self.unet.attn_processors.values():                     # :319-322
             if isinstance(attn_processor, IPAttnProcessor):
                 conditioning_scale = attn_processor.scale
                 break
-        out = self.engine.run(lat, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
-                              negative_pooled_prompt_embeds, add_time_ids, num_inference_steps,
-                              guidance_scale=guidance_scale, ip_scale=conditioning_scale,
-                              control_guidance_start=control_guidance_start, control_guidance_end=control_guidance_end)
+        if loop_steps > 0:
+            out = self.engine.run(lat, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
+                                  negative_pooled_prompt_embeds, add_time_ids, num_inference_steps,
+                                  guidance_scale=guidance_scale, ip_scale=conditioning_scale,
+                                  control_guidance_start=control_guidance_start,
+                                  control_guidance_end=control_guidance_end, guidance_rescale=guidance_rescale,
+                                  num_loop_steps=loop_steps, callback=callback, callback_steps=callback_steps,
+                                  negative_time_ids=negative_add_time_ids)
+        else:
+            out = lat.to(self.device)
         self.set_scale(conditioning_scale)
         if output_type == "latent":
             image = out

@@ -138,7 +138,12 @@ class IPAdapter:
         else:
             parts = torch.load(self.ip_ckpt, map_location="cpu")                   # the 3-key dict of convert_bin.py
         self.image_proj_model.load_state_dict(parts["image_proj"])
-        if self.number_class_crossattention is not None and parts.get("composed_adapter"):
+        if self.number_class_crossattention is not None:
+            if not parts.get("composed_adapter"):
+                # the reference loads this part strictly (:151-152): a HarmonyAttention module without its weights would
+                # add a residual from random parameters to every image embedding
+                raise KeyError("composed_adapter: number_class_crossattention was given but the checkpoint holds no "
+                               "HarmonyAttention weights")
             self.number_class_crossattention.load_state_dict(parts["composed_adapter"])
         # strict and index-keyed: every one of the 70 cross-attention processors owns to_k_ip / to_v_ip (:153)
         torch.nn.ModuleList(self.pipe.unet.attn_processors.values()).load_state_dict(parts["ip_adapter"])

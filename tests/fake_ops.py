@@ -214,11 +214,38 @@ def euler_cfg_step(noise_pred, latents, model_in, sigmas, step, guidance):
     step += 1
 
 
-def scale_model_input(latents, model_in, sigmas, step):
+def workspace_generation():
+    return 0
+
+
+def euler_step(noise_pred, latents, model_in, sigmas, step, guidance, *, use_cfg=True, guidance_rescale=0.0):
+    if use_cfg and not guidance_rescale:
+        return euler_cfg_step(noise_pred, latents, model_in, sigmas, step, guidance)
+    _count[0] += 2
+    i = int(step.item())
+    s, sn = float(sigmas[i]), float(sigmas[i + 1])
+    if use_cfg:
+        u, c = noise_pred.chunk(2)
+        eps = u + guidance * (c - u)
+        dims = list(range(1, eps.dim()))
+        resc = eps * (c.std(dim=dims, keepdim=True) / eps.std(dim=dims, keepdim=True))
+        eps = guidance_rescale * resc + (1 - guidance_rescale) * eps
+    else:
+        eps = noise_pred
+    x = latents.float()
+    x0 = x - (s * eps.float()).to(eps.dtype).float()
+    xn = (x + (x - x0) / s * (sn - s)).to(latents.dtype)
+    latents.copy_(xn)
+    mi = (xn.float() / (sn * sn + 1) ** 0.5).to(model_in.dtype)
+    model_in.copy_(torch.cat([mi, mi]) if use_cfg else mi)
+    step += 1
+
+
+def scale_model_input(latents, model_in, sigmas, step, duplicate=True):
     _count[0] += 1
     s = float(sigmas[int(step.item())])
     mi = (latents.float() / (s * s + 1) ** 0.5).to(model_in.dtype)
-    model_in.copy_(torch.cat([mi, mi]))
+    model_in.copy_(torch.cat([mi, mi]) if duplicate else mi)
 
 
 def im2col3x3_nchw(x_nchw, kpad=64, out=None):

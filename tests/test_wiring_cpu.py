@@ -218,3 +218,157 @@ def test_ip_adapter_plus_xl_generate_call_surface(patched):
     out = model.generate(prompt="lions", num_samples=2, num_inference_steps=1, seed=[1, 2], clip_hidden_states=hs,
                          uncond_clip_hidden_states=un, output_type="latent", height=128, width=128)
     assert out.shape == (2, 4, 16, 16) and torch.isfinite(out.float()).all()
+
+
+def _fp32_engine(native):
+    """DenoiseEngine on the CPU stand-in ops with fp32 static buffers (wiring tests compare to fp32 round-off)."""
+    from imagharmony_b200.denoise import DenoiseEngine
+    return DenoiseEngine(native, use_cuda_graph=False)
+
+
+class _Empty32:
+    """Context manager: torch.empty(dtype=float16) inside imagharmony_b200.denoise allocates fp32 instead."""
+
+    def __enter__(self):
+        import imagharmony_b200.denoise as dn
+        self.dn, self.orig = dn, torch.empty
+
+        def empty32(*a, **k):
+            if k.get("dtype") == torch.float16:
+                k["dtype"] = torch.float32
+            return self.orig(*a, **k)
+        dn.torch.empty = empty32
+
+    def __exit__(self, *a):
+        self.dn.torch.empty = self.orig
+
+
+@pytest.mark.parametrize("opts", [
+    dict(guidance_scale=1.0),                                   # custom_pipelines.py:223 -- no classifier-free guidance
+    dict(guidance_scale=5.0, guidance_rescale=0.7),             # :352-354
+    dict(guidance_scale=5.0, denoising_end=0.5),                # :307-316
+    dict(guidance_scale=0.5, denoising_end=0.7),
+])
+def test_denoise_loop_options_match_oracle(patched, opts):
+    """The loop options the reference accepts (no CFG, guidance_rescale, denoising_end, callback) through the native
+    engine on the stand-in ops vs the oracle loop."""
+    from imagharmony_b200.config import TINY
+    from oracle.scheduler_ref import denoise_loop, denoising_end_steps, euler_tables, prepare_latents
+    native, ref = _build(TINY, 4)
+    T, n, lat = 4, 2, 8
+    _, _, ins = euler_tables(T)
+    latents = prepare_latents(n, 4, lat, lat, [5, 6], ins, dtype=torch.float32)
+    _, ehs, te, tid = _inputs(TINY, n, lat, seed=9)
+    procs = [p for p in ref.attn_processors.values() if hasattr(p, "to_k_ip")]
+
+    def set_scale(s):
+        for p in procs:
+            p.scale = s
+    seen_ref, seen = [], []
+    r = denoise_loop(lambda s, t, e, x, y: ref(s, t, e, x, y), latents.clone(), ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T,
+                     set_scale=set_scale, conditioning_scale=0.8, control_guidance_end=0.75,
+                     callback=lambda i, t, x: seen_ref.append((i, float(t), x.clone())), callback_steps=2, **opts)
+    eng = _fp32_engine(native)
+    kw = dict(opts)
+    de = kw.pop("denoising_end", None)
+    loop_steps = denoising_end_steps(T, de)
+    with _Empty32():
+        o = eng.run(latents.clone(), ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T, ip_scale=0.8, control_guidance_end=0.75,
+                    num_loop_steps=loop_steps, callback=lambda i, t, x: seen.append((i, float(t), x.clone())),
+                    callback_steps=2, **kw)
+    assert torch.allclose(o, r, rtol=3e-4, atol=1e-3), (o - r).abs().max()    # fp32 round-off at |latent| ~ 10
+    assert [s[0] for s in seen] == [s[0] for s in seen_ref] and [s[1] for s in seen] == [s[1] for s in seen_ref]
+    for a, b in zip(seen, seen_ref):
+        assert torch.allclose(a[2], b[2], rtol=3e-4, atol=1e-3)
+
+
+def test_pipeline_forwards_loop_options(patched):
+    """StableDiffusionXLCustomPipeline.__call__ accepts what the reference accepts (custom_pipelines.py:23-56):
+    guidance_scale <= 1, guidance_rescale, denoising_end, callback, negative micro-conditioning -- no IHError."""
+    from imagharmony_b200.config import TINY
+    from ip_adapter.custom_pipelines import StableDiffusionXLCustomPipeline
+    pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu")
+    pe, ne = torch.randn(1, 81, TINY.cross_attention_dim).half(), torch.randn(1, 81, TINY.cross_attention_dim).half()
+    pp, npool = torch.randn(1, TINY.pooled_embed_dim).half(), torch.randn(1, TINY.pooled_embed_dim).half()
+    calls = []
+    common = dict(prompt_embeds=pe, negative_prompt_embeds=ne, pooled_prompt_embeds=pp, negative_pooled_prompt_embeds=npool,
+                  num_inference_steps=4, output_type="latent", height=64, width=64,
+                  generator=torch.Generator("cpu").manual_seed(1))
+    a = pipe(guidance_scale=5.0, guidance_rescale=0.5, callback=lambda i, t, x: calls.append(i), callback_steps=1,
+             negative_original_size=(32, 32), negative_target_size=(64, 64), **common).images
+    assert calls == [0, 1, 2, 3] and torch.isfinite(a.float()).all()
+    common["generator"] = torch.Generator("cpu").manual_seed(1)
+    calls.clear()
+    b = pipe(guidance_scale=1.0, denoising_end=0.5, callback=lambda i, t, x: calls.append(i), **common).images
+    assert calls == [0, 1] and torch.isfinite(b.float()).all() and not torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pipe(guidance_scale=5.0, callback=lambda *a: None, callback_steps=0, **common)
+    # the engine integrates the pipeline's own scheduler object (a replaced scheduler rebuilds the engine)
+    from imagharmony_b200.scheduler import EulerDiscreteScheduler
+    e0 = pipe.engine
+    assert e0.scheduler is pipe.scheduler
+    pipe.scheduler = EulerDiscreteScheduler(beta_end=0.02)
+    assert pipe.engine is not e0 and pipe.engine.scheduler is pipe.scheduler
+    from imagharmony_b200._lib import IHError
+    with pytest.raises(IHError):
+        pipe.to("cuda:1")
+
+
+def test_step_invariant_buffers_are_per_shape(patched):
+    """K/V and add-embedding buffers a captured graph reads must survive a change of batch size.
+    n=1 -> n=2 -> n=1 through one engine: every (processor, shape) keeps ONE buffer address, and the trajectory of the
+    second n=1 call equals the first."""
+    from imagharmony_b200.config import TINY
+    from oracle.scheduler_ref import euler_tables, prepare_latents
+    native, _ = _build(TINY, 6)
+    T, lat = 2, 8
+    _, _, ins = euler_tables(T)
+    eng = _fp32_engine(native)
+    procs = [p for p in native.attn_processors.values() if hasattr(p, "to_k_ip")]
+
+    def run(n, seeds):
+        latents = prepare_latents(n, 4, lat, lat, seeds, ins, dtype=torch.float32)
+        _, ehs, te, tid = _inputs(TINY, n, lat, seed=11)
+        with _Empty32():
+            return eng.run(latents, ehs[n:], ehs[:n], te[n:], te[:n], tid[:n], T)
+    a = run(1, [3])
+    ptr1 = [p._kv[1].data_ptr() for p in procs]
+    aug1 = native._aug[1].data_ptr()
+    run(2, [3, 4])
+    ptr2 = [p._kv[1].data_ptr() for p in procs]
+    assert all(x != y for x, y in zip(ptr1, ptr2)) and native._aug[1].data_ptr() != aug1
+    b = run(1, [3])
+    assert [p._kv[1].data_ptr() for p in procs] == ptr1 and native._aug[1].data_ptr() == aug1
+    assert torch.equal(a, b)
+    epoch = native.graph_epoch
+    native.finalize()
+    assert native.graph_epoch > epoch and all(not p._kv_bufs for p in procs)
+
+
+def test_harmony_attention_groups_text_rows_per_image(patched):
+    """encode_prompt(extra_text, num_images_per_prompt=n) returns rows [a,a,b,b]; image i must attend
+    to ITS text (the reference's Cross_Attention view(B, -1, D) groups [a,a],[b,b]) -- checked against the oracle
+    restatement of train.py:243-266 that is pinned to the reference class."""
+    from imagharmony_b200 import adapter as N
+    from imagharmony_b200.config import HARMONY_TINY as h
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    from oracle.adapter_ref import HarmonyAttentionRef
+    kw = dict(image_hidden_size=h.image_hidden_size, text_context_dim=h.text_context_dim, inter_dim=h.inter_dim,
+              cross_heads=h.cross_heads, reshape_blocks=h.reshape_blocks, cross_value_dim=h.cross_value_dim)
+    ha = N.HarmonyAttention(fusion_method="cross_attention", **kw)
+    sd = {k: v.float() for k, v in random_state_dict(shapes_of(ha), 12).items()}
+    ha.load_state_dict(sd)
+    ref = HarmonyAttentionRef(**kw)
+    ref.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    img = torch.randn(2, h.image_hidden_size, generator=g)
+    ta, tb = torch.randn(1, 7, h.text_context_dim, generator=g), torch.randn(1, 7, h.text_context_dim, generator=g)
+    text = torch.cat([ta, ta, tb, tb])                       # num_samples = 2 copies per image, copies adjacent
+    with torch.no_grad():
+        want = ref(text, img)
+        got = ha(text, img)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    # image 1 really uses text b (a wrong grouping -- text[:B] -- gives image 1 the text of image 0)
+    with torch.no_grad():
+        wrong = ref(torch.cat([ta, ta]), img)
+    assert (wrong[1] - want[1]).abs().max() > 1e-3
