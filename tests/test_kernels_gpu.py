@@ -452,3 +452,36 @@ def test_euler_cfg_step(ops):
     m2 = torch.empty_like(model_in)
     ops.scale_model_input(lat, m2, sig, step)
     check(m2, torch.cat([mi, mi]), "scale_model_input")
+
+
+@pytest.mark.parametrize("use_cfg,rescale", [(False, 0.0), (True, 0.7), (True, 1.0)])
+def test_euler_step_ex(ops, use_cfg, rescale):
+    """ih_euler_step_ex: no-CFG (custom_pipelines.py:223) and guidance_rescale (:352-354) variants of the transition,
+    against the fp16 tensor arithmetic of the reference loop (oracle/scheduler_ref.py rescale_noise_cfg)."""
+    from oracle.scheduler_ref import rescale_noise_cfg
+    n, H = 3, 64
+    b = 2 * n if use_cfg else n
+    lat = rnd(n, 4, H, H) * 5
+    noise = rnd(b, 4, H, H, seed=2)
+    sig = torch.tensor([13.1204, 11.6761, 10.4250, 0.0], device="cuda")
+    step = torch.tensor([1], dtype=torch.int32, device="cuda")
+    model_in = torch.empty(b, 4, H, H, dtype=torch.float16, device="cuda")
+    lat_ref = lat.clone()
+    ops.euler_step(noise, lat, model_in, sig, step, 5.0, use_cfg=use_cfg, guidance_rescale=rescale)
+    if use_cfg:
+        u, c = noise.chunk(2)
+        eps = u + 5.0 * (c - u)
+        eps = rescale_noise_cfg(eps, c, rescale)          # fp16 tensors -> fp16 rounding points
+    else:
+        eps = noise
+    x = lat_ref.float()
+    x0 = x - (sig[1] * eps.float()).half().float()
+    xn = (x + (x - x0) / sig[1] * (sig[2] - sig[1])).half()
+    assert int(step.item()) == 2
+    # sigma ~ 11.7 amplifies one fp16 ulp of eps (the std ratio is itself an fp16 number): 2e-3 relative on |x| ~ 20
+    check(lat, xn, f"euler_ex latents cfg={use_cfg} r={rescale}", rtol=2e-3, atol=2e-3)
+    mi = (lat.float() / (sig[2] ** 2 + 1) ** 0.5).half()
+    check(model_in, torch.cat([mi, mi]) if use_cfg else mi, "euler_ex model_in")
+    m2 = torch.empty_like(model_in)
+    ops.scale_model_input(lat, m2, sig, step, duplicate=use_cfg)
+    check(m2, torch.cat([mi, mi]) if use_cfg else mi, "scale_model_input_ex")

@@ -114,3 +114,32 @@ def test_unet_ref_tiny_forward_runs():
         out = m(torch.randn(2, 4, 16, 16), 500.0, torch.randn(2, 9 + 4, TINY.cross_attention_dim),
                 torch.randn(2, TINY.pooled_embed_dim), torch.tensor([[128., 128, 0, 0, 128, 128]] * 2))
     assert out.shape == (2, 4, 16, 16) and torch.isfinite(out).all()
+
+
+def test_oracle_matches_reference_at_real_shapes():
+    """The oracle restatement against the reference's own classes at the REAL shapes (tests/golden/
+    reference_real_shapes.pt, written by oracle/make_real_shape_goldens.py from /root/reference): the a1 layer
+    (C 1280, 20 heads, N 1024, 77 + 4 tokens), HarmonyAttention at the shipped sizes, ImageProjModel."""
+    import os
+    from oracle import adapter_ref as A
+    from oracle import make_real_shape_goldens as G
+    from oracle.unet_ref import Attention
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_real_shapes.pt"), map_location="cpu")
+    idx, (name, _, C, H, N, skip, stride) = 0, G.ATTN_CASES[0]
+    assert name == "ipattn_a1" and not skip
+    hidden, ehs = G.attn_case_inputs(idx, C, N)
+    attn = Attention(C, H, G.CROSS_DIM)
+    attn.load_state_dict({k: v.float() for k, v in G.state_for(attn, 300 + idx).items()})
+    proc = A.IPAttnProcessorRef(C, G.CROSS_DIM, scale=G.IP_SCALE, num_tokens=G.N_IP, skip=False)
+    proc.load_state_dict({k: v.float() for k, v in G.state_for(proc, 400 + idx).items()})
+    with torch.no_grad():
+        y = proc(attn, hidden.float(), encoder_hidden_states=ehs.float())
+    assert (y[:, ::stride] - gold[name]["out"]).abs().max() < 2e-5
+    ha = A.HarmonyAttentionRef(**G.HARMONY_KW)
+    ha.load_state_dict({k: v.float() for k, v in G.state_for(ha, 500).items()})
+    text, img = G.seeded((1, G.N_TEXT, G.CROSS_DIM), 501), G.seeded((1, 1280), 502)
+    with torch.no_grad():
+        assert (ha(text.float(), img.float()) - gold["harmony"]["out"]).abs().max() < 2e-5
+        ip = A.ImageProjRef(G.CROSS_DIM, 1280, G.N_IP)
+        ip.load_state_dict({k: v.float() for k, v in G.state_for(ip, 510).items()})
+        assert (ip(img.float()) - gold["imageproj"]["out"]).abs().max() < 2e-5
