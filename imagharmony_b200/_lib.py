@@ -14,8 +14,45 @@ LIB_NAME = "libimagharmony_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+_SRC_DIRS = (os.path.join(_HERE, "csrc"), os.path.join(os.path.dirname(_HERE), "include"))
+
+
 class IHError(RuntimeError):
     pass
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA / header sources the library is built from (name + content, sorted)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in _SRC_DIRS:
+        for name in sorted(os.listdir(d)):
+            if name.endswith((".cu", ".cuh", ".h")) or name == "Makefile":
+                h.update(name.encode())
+                with open(os.path.join(d, name), "rb") as f:
+                    h.update(f.read())
+    return h.hexdigest()
+
+
+def write_source_hash() -> None:
+    """Called by __graft_entry__.build() after a successful `make`: records which sources the binary was built from."""
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
+
+
+def _check_fresh() -> None:
+    """A stale binary must never be tested or benchmarked: the library is refused unless it was built from exactly the
+    sources in the tree (IH_SKIP_SRCHASH=1 overrides, for debugging only)."""
+    if os.environ.get("IH_SKIP_SRCHASH", "0") == "1":
+        return
+    if not os.path.exists(HASH_PATH):
+        raise IHError(f"{LIB_NAME} has no source hash next to it: rebuild with `python -c 'import __graft_entry__ as g; "
+                      "g.build()'`")
+    built = open(HASH_PATH).read().strip()
+    if built != source_hash():
+        raise IHError(f"{LIB_NAME} is STALE: csrc/ or include/ changed since it was built; rebuild with "
+                      "`python -c 'import __graft_entry__ as g; g.build()'`")
 
 
 # name -> (restype, argtypes); must list every symbol of include/ih_api.h (tests/test_abi.py checks this)
@@ -81,6 +118,7 @@ def load() -> ctypes.CDLL:
         raise IHError(
             f"{LIB_NAME} not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C imagharmony_b200/csrc` (there is no CPU fallback)")
+    _check_fresh()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         try:

@@ -27,16 +27,30 @@ def shard_seeds(seeds: Sequence[int], rank: int, world: int) -> List[int]:
 
 
 class LinearProbeScorer:
-    """Synthetic judge (no CLIP / VLM weights exist offline): a fixed random linear probe of the candidate latent,
-    score_i = <w, x_i> / ||w||.  Deterministic in `seed`, identical on every rank."""
+    """Synthetic judge for environments without CLIP / VLM weights: a fixed random linear probe of the candidate
+    latent, score_i = <w, x_i> / ||w||.  Deterministic in `seed`, identical on every rank.  On the GPU the probe is
+    one launch of the library's weight-streaming small-M kernel (`ih_linear_small_f16`); CPU tensors (gloo tests) use
+    a plain dot product.  `imagharmony_b200.clip.ClipScorer` is the real judge (image-text cosine of the CLIP towers)."""
 
     def __init__(self, numel: int, seed: int = 1234, device="cpu"):
         g = torch.Generator("cpu").manual_seed(seed)
         w = torch.randn(numel, generator=g)
         self.w = (w / w.norm()).to(device)
+        self._w16 = None
+
+    def describe(self) -> str:
+        return "fixed random linear probe of the final latent (synthetic judge, no CLIP weights offline)"
 
     def __call__(self, latents: torch.Tensor) -> torch.Tensor:
-        return latents.reshape(latents.shape[0], -1).float() @ self.w.to(latents.device)
+        x = latents.reshape(latents.shape[0], -1)
+        if x.is_cuda and x.dtype == torch.float16 and x.shape[0] <= 64:
+            from . import ops
+            if self._w16 is None or self._w16.device != x.device:
+                # 8 output rows (16-byte rows for the kernel), row 0 carries the probe scaled into fp16's normal range
+                self._w16 = torch.zeros((8, x.shape[1]), dtype=torch.float16, device=x.device)
+                self._w16[0] = (self.w.to(x.device) * 64.0).half()
+            return ops.linear_small(x.contiguous(), self._w16)[:, 0].float() / 64.0
+        return x.float() @ self.w.to(latents.device)
 
 
 @dataclass
