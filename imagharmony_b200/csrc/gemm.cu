@@ -51,7 +51,7 @@ struct GemmParams {
   long long ldr;
   __half* out;
   long long ldo;
-  int act;  // 0 none, 1 SiLU, 2 GELU(erf) (applied after bias, before residual)
+  int act;  // 0 none, 1 SiLU, 2 GELU(erf), 3 quick-GELU (applied after bias, before residual)
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA 0 (ih_gemm_set_trace), nullptr in production
   // LayerNorm folding (plain GEMM mode only).  A producer GEMM writes, per output row and 64-column slab, the sum and
   // the sum of squares of the fp16-rounded values it stores (stats_out [ceil(N/64), M, 2] fp32, one writer per slot:
@@ -447,6 +447,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               } else if (p.act == 2) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
+              } else if (p.act == 3) {   // quick_gelu x * sigmoid(1.702 x) ([3P] CLIP-L text tower MLP)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = __fdividef(x[e], 1.f + __expf(-1.702f * x[e]));
               }
               uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ rx) << 4));
               if (p.residual) {
@@ -677,7 +680,7 @@ extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const
   p.ldr = ldr;
   p.out = (__half*)out;
   p.ldo = ldo;
-  p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : 0);
+  p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : ((epilogue & IH_EPI_QUICK_GELU) ? 3 : 0));
   p.trace = g_trace;
   IH_CHECK(!ln_stats || ln_slabs > 0, IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_slabs > 0");
   IH_CHECK(!stats_out || N % 64 == 0 || geglu, IH_ERR_SHAPE, "ih_gemm_ln_f16: stats_out needs N %% 64 == 0");

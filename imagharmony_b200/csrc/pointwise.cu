@@ -425,6 +425,126 @@ __global__ void attention_small_kernel(const __half* __restrict__ q, long long l
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Generic SDPA for the CLIP towers (scope row f2: [3P] transformers CLIPAttention as the reference calls it through
+// ip_adapter.py:81-84,163-164 (vision, head_dim 104 for ViT-bigG) and encode_prompt :292-319 (text, causal mask)):
+// softmax(q k^T * scale [+ causal mask]) v with fp32 scores / softmax, one warp per (batch, head, query); keys are
+// strided over the lanes with 16-byte loads, the PV sweep gives each lane dv/32 output channels.  head dims % 8 == 0.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void attention_generic_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k,
+                                         long long ldk, const __half* __restrict__ v, long long ldv,
+                                         __half* __restrict__ out, long long ldo, int H, int Nq, int Nk, int dqk, int dv,
+                                         float scale, int causal, long long total_warps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_p[];  // [warps][Nk]
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;  // (b, h, iq)
+  if (gw >= total_warps) return;
+  const int iq = (int)(gw % Nq);
+  const int h = (int)((gw / Nq) % H);
+  const int b = (int)(gw / ((long long)Nq * H));
+  float* p = s_p + warp_in_block * Nk;
+  const __half* qr = q + ((long long)b * Nq + iq) * ldq + h * dqk;
+  const int nk_live = causal ? min(Nk, iq + 1 + (Nk - Nq)) : Nk;   // key j visible iff j <= iq (+ offset when Nk > Nq)
+  float mx = -INFINITY;
+  for (int j = lane; j < nk_live; j += 32) {
+    const __half* kr = k + ((long long)b * Nk + j) * ldk + h * dqk;
+    float acc = 0.f;
+    for (int d = 0; d < dqk; d += 8) {
+      float a[8], c[8];
+      ld8(qr + d, a);
+      ld8(kr + d, c);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(a[e], c[e], acc);
+    }
+    acc *= scale;
+    p[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < nk_live; j += 32) {
+    const float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  for (int d = lane; d < dv; d += 32) {
+    float acc = 0.f;
+    const __half* vc = v + (long long)b * Nk * ldv + h * dv + d;
+    for (int j = 0; j < nk_live; ++j) acc = fmaf(p[j], __half2float(vc[(long long)j * ldv]), acc);
+    out[((long long)b * Nq + iq) * ldo + h * dv + d] = __float2half_rn(acc * inv);
+  }
+}
+
+// out[b, t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]   ([3P] CLIPTextEmbeddings; one 16-byte vector per thread)
+__global__ void embed_tokens_kernel(const int* __restrict__ ids, const __half* __restrict__ tok, const __half* __restrict__ pos,
+                                    __half* __restrict__ out, int rows, int T, int C8, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)rows * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C8), c = (int)(i - (long long)r * C8);
+    int id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint4 a = reinterpret_cast<const uint4*>(tok)[(long long)id * C8 + c];
+    const uint4 b = reinterpret_cast<const uint4*>(pos)[(long long)(r % T) * C8 + c];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_half2(aw[e]), g = unpack_half2(bw[e]);
+      o[e] = pack_half2(f.x + g.x, f.y + g.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// CLIP-scorer front end (PNS judge): decoded image NCHW fp16 in [-1, 1] -> area-averaged S x S image -> [0, 1] ->
+// (v - mean[c]) / std[c] -> patch rows [B * (S/P)^2, Kpad] with k = c*P*P + py*P + px (the layout of the flattened
+// CLIP patch_embedding conv weight), zero padded to Kpad.  One thread per output pixel and channel.
+__global__ void resize_patchify_kernel(const __half* __restrict__ img, __half* __restrict__ out, int B, int C, int Hin,
+                                       int Win, int S, int P, int Kpad, float m0, float m1, float m2, float s0, float s1,
+                                       float s2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int G = S / P;
+  const long long total = (long long)B * G * G * Kpad;
+  const float fy = (float)Hin / (float)S, fx = (float)Win / (float)S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % Kpad);
+    const long long row = i / Kpad;
+    if (kk >= C * P * P) {
+      out[i] = __float2half_rn(0.f);
+      continue;
+    }
+    const int c = kk / (P * P), py = (kk / P) % P, px = kk % P;
+    const int gx = (int)(row % G), gy = (int)((row / G) % G), b = (int)(row / ((long long)G * G));
+    const int oy = gy * P + py, ox = gx * P + px;
+    const float y0 = oy * fy, y1 = (oy + 1) * fy, x0 = ox * fx, x1 = (ox + 1) * fx;
+    const int iy0 = (int)floorf(y0), iy1 = min(Hin, (int)ceilf(y1)), ix0 = (int)floorf(x0), ix1 = min(Win, (int)ceilf(x1));
+    const __half* src = img + ((long long)b * C + c) * Hin * Win;
+    float acc = 0.f, wsum = 0.f;
+    for (int y = iy0; y < iy1; ++y) {
+      const float wy = fminf(y1, (float)(y + 1)) - fmaxf(y0, (float)y);
+      for (int x = ix0; x < ix1; ++x) {
+        const float wx = fminf(x1, (float)(x + 1)) - fmaxf(x0, (float)x);
+        acc = fmaf(wy * wx, __half2float(src[(long long)y * Win + x]), acc);
+        wsum += wy * wx;
+      }
+    }
+    float vpx = fminf(fmaxf(acc / wsum * 0.5f + 0.5f, 0.f), 1.f);
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    out[i] = __float2half_rn((vpx - mean) / sd);
+  }
+}
+
 // out[i] = a[i] + b[i % period]  (16-byte vectors; period in elements, multiple of 8)
 __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                                  long long nvec, long long period_vec) {
@@ -720,6 +840,52 @@ extern "C" int ih_attention_small_f16(const void* q, long long ldq, const void* 
   IH_CUDA(launch_kernel(attention_small_kernel, dim3(blocks), dim3(warps * 32), (size_t)(warps * Nk * sizeof(float)), (cudaStream_t)stream, 
       (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo, H, Nq, Nk, dqk, dv,
       scale));
+  return 0;
+}
+
+extern "C" int ih_attention_generic_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                        long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk, int dqk,
+                                        int dv, float scale, int causal, void* stream) {
+  IH_CHECK(q && k && v && out, IH_ERR_ARG, "ih_attention_generic_f16: null pointer");
+  IH_CHECK(Nk >= 1 && Nk <= 4096 && Nq >= 1 && dqk >= 8 && dqk <= 256 && dv >= 1 && dv <= 256 && dqk % 8 == 0 &&
+               ldq % 8 == 0 && ldk % 8 == 0, IH_ERR_SHAPE,
+           "ih_attention_generic_f16: Nk <= 4096, head dims <= 256, dqk / ldq / ldk multiples of 8 required");
+  IH_CHECK(!causal || Nk >= Nq, IH_ERR_SHAPE, "ih_attention_generic_f16: causal needs Nk >= Nq");
+  const int warps = 4;
+  const long long total = (long long)B * H * Nq;
+  const int blocks = (int)((total + warps - 1) / warps);
+  const size_t smem = (size_t)warps * Nk * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    IH_CUDA(cudaFuncSetAttribute(attention_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4));
+    configured = true;
+  }
+  IH_CUDA(launch_kernel(attention_generic_kernel, dim3(blocks), dim3(warps * 32), smem, (cudaStream_t)stream,
+                        (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo, H, Nq, Nk,
+                        dqk, dv, scale, causal ? 1 : 0, total));
+  return 0;
+}
+
+extern "C" int ih_embed_tokens_f16(const void* ids_i32, const void* tok_emb, const void* pos_emb, void* out, int rows,
+                                   int T, int C, int vocab, void* stream) {
+  IH_CHECK(ids_i32 && tok_emb && pos_emb && out, IH_ERR_ARG, "ih_embed_tokens_f16: null pointer");
+  IH_CHECK(rows > 0 && T > 0 && C % 8 == 0 && vocab > 0, IH_ERR_SHAPE, "ih_embed_tokens_f16: bad shape");
+  const long long total = (long long)rows * (C / 8);
+  IH_CUDA(launch_kernel(embed_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        (const int*)ids_i32, (const __half*)tok_emb, (const __half*)pos_emb, (__half*)out, rows, T, C / 8,
+                        vocab));
+  return 0;
+}
+
+extern "C" int ih_resize_patchify_f16(const void* img_nchw, void* out, int B, int C, int Hin, int Win, int S, int P,
+                                      int Kpad, const float* mean3, const float* std3, void* stream) {
+  IH_CHECK(img_nchw && out && mean3 && std3, IH_ERR_ARG, "ih_resize_patchify_f16: null pointer");
+  IH_CHECK(C == 3 && S % P == 0 && Kpad % 8 == 0 && Kpad >= C * P * P && Hin > 0 && Win > 0, IH_ERR_SHAPE,
+           "ih_resize_patchify_f16: 3 channels, S %% P == 0, Kpad >= 3*P*P (multiple of 8) required");
+  const long long total = (long long)B * (S / P) * (S / P) * Kpad;
+  IH_CUDA(launch_kernel(resize_patchify_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        (const __half*)img_nchw, (__half*)out, B, C, Hin, Win, S, P, Kpad, mean3[0], mean3[1], mean3[2],
+                        std3[0], std3[1], std3[2]));
   return 0;
 }
 

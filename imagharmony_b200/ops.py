@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import IHError, check
 
-EPI_NONE, EPI_GEGLU, EPI_SILU, EPI_GELU = 0, 1, 2, 4
+EPI_NONE, EPI_GEGLU, EPI_SILU, EPI_GELU, EPI_QUICK_GELU = 0, 1, 2, 4, 8
 
 
 def _stream() -> int:
@@ -51,7 +51,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
            rows_per_group: int = 0, geglu: bool = False, silu: bool = False, gelu: bool = False,
            out: Optional[torch.Tensor] = None, tile_n: int = 0, ln=None,
-           stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           stats_out: Optional[torch.Tensor] = None, quick_gelu: bool = False) -> torch.Tensor:
     """out = epi(x @ w.T + bias + rowbias[row // rows_per_group]) + residual ; x [M,K], w [N,K] (nn.Linear layout).
 
     LayerNorm folding: `stats_out` (float32 [ceil(N/64), M, 2]) receives per-row / per-64-column (sum, sumsq) of the
@@ -68,7 +68,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
     ldr = _rows(residual, "residual") if residual is not None else 0
     ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
-    epi = (EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0) | (EPI_GELU if gelu else 0)
+    epi = ((EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0) | (EPI_GELU if gelu else 0)
+           | (EPI_QUICK_GELU if quick_gelu else 0))
     if ln is None and stats_out is None:
         rc = lib.ih_gemm_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(rowbias), rows_per_group, ldrb,
                              _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _stream())
@@ -309,6 +310,57 @@ def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H
                                     _rows(v, "v"), out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, dqk, dv,
                                     float(scale), _stream())
     check(rc, "ih_attention_small_f16")
+    return out
+
+
+def attention_generic(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Nq: int, Nk: int, dqk: int,
+                      dv: int, scale: float, causal: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale (+ causal mask)) v for any head dims that are multiples of 8 (CLIP towers: 64 causal,
+    104 for ViT-bigG): q [B*Nq, >=H*dqk], k [B*Nk, >=H*dqk], v [B*Nk, >=H*dv] 2-D views."""
+    lib = _lib.load()
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    if out is None:
+        out = torch.empty((B * Nq, H * dv), dtype=torch.float16, device=q.device)
+    rc = lib.ih_attention_generic_f16(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(),
+                                      _rows(v, "v"), out.data_ptr(), _rows(out, "out"), B, H, Nq, Nk, dqk, dv,
+                                      float(scale), int(causal), _stream())
+    check(rc, "ih_attention_generic_f16")
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ids int32 [B, T] (device) -> tok_emb[ids] + pos_emb[:T]  as [B*T, C] fp16."""
+    lib = _lib.load()
+    _req(ids, "ids", torch.int32); _req(tok_emb, "tok_emb"); _req(pos_emb, "pos_emb")
+    B, T = ids.shape
+    C = tok_emb.shape[1]
+    if not (ids.is_contiguous() and tok_emb.is_contiguous() and pos_emb.is_contiguous()) or pos_emb.shape[0] < T:
+        raise IHError("embed_tokens: contiguous ids / tables and pos_emb with >= T rows required")
+    if out is None:
+        out = torch.empty((B * T, C), dtype=torch.float16, device=ids.device)
+    check(lib.ih_embed_tokens_f16(ids.data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), out.data_ptr(), B * T, T, C,
+                                  tok_emb.shape[0], _stream()), "ih_embed_tokens_f16")
+    return out
+
+
+def resize_patchify(img: torch.Tensor, size: int, patch: int, kpad: int, mean, std,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """img NCHW fp16 in [-1, 1] -> area-averaged size x size, [0,1], (v - mean) / std, as patch rows
+    [B * (size/patch)^2, kpad] with k = c*patch^2 + py*patch + px (zero padded)."""
+    import ctypes
+    lib = _lib.load()
+    _req(img, "img")
+    B, C, H, W = img.shape
+    if not img.is_contiguous():
+        raise IHError("resize_patchify: contiguous NCHW image required")
+    g = size // patch
+    if out is None:
+        out = torch.empty((B * g * g, kpad), dtype=torch.float16, device=img.device)
+    m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
+    s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
+    check(lib.ih_resize_patchify_f16(img.data_ptr(), out.data_ptr(), B, C, H, W, size, patch, kpad, m3, s3, _stream()),
+          "ih_resize_patchify_f16")
     return out
 
 

@@ -25,6 +25,7 @@ extern "C" {
 #define IH_EPI_GEGLU 1 /* out[:, j] = (acc[:, j] + b[j]) * gelu_erf(acc[:, F + j] + b[F + j]),  N = 2F */
 #define IH_EPI_SILU 2  /* out = silu(acc + bias) */
 #define IH_EPI_GELU 4  /* out = gelu_erf(acc + bias) */
+#define IH_EPI_QUICK_GELU 8 /* out = x * sigmoid(1.702 x), x = acc + bias  (CLIP-L text tower MLP, scope row f2) */
 
 const char* ih_last_error(void);
 int ih_version(void);
@@ -169,6 +170,26 @@ int ih_nhwc_to_nchw_f16(const void* x, long long ldc, void* out, int B, long lon
  * sigmas: device fp32 [T+1]; step: device int32 (read, then incremented). n_per_image = 4*H*W. */
 int ih_euler_cfg_step(const void* noise_pred, void* latents, void* model_in, const void* sigmas, void* step,
                       float guidance, long long n_per_image, int n_images, void* stream);
+
+/* ---- scope row f2: conditioning encoders (CLIP towers the reference loads at ip_adapter.py:81-84 and calls at
+ * :163-164 (image) and through encode_prompt :292-319 (text)); arithmetic = [3P] transformers CLIPEncoderLayer. ---- */
+
+/* softmax(q k^T * scale (+ causal mask)) v, any head dims that are multiples of 8 (<= 256), fp32 softmax.
+ * q [B*Nq, >= H*dqk], k [B*Nk, >= H*dqk], v [B*Nk, >= H*dv], out [B*Nq, >= H*dv]; causal: key j visible iff j <= i.
+ * Replaces CLIPAttention (text: causal, head_dim 64; ViT-bigG vision: head_dim 104). */
+int ih_attention_generic_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                             void* out, long long ldo, int B, int H, int Nq, int Nk, int dqk, int dv, float scale,
+                             int causal, void* stream);
+
+/* out[r, :] = tok_emb[ids[r], :] + pos_emb[r % T, :]   (CLIPTextEmbeddings); ids int32 device [rows]. */
+int ih_embed_tokens_f16(const void* ids_i32, const void* tok_emb, const void* pos_emb, void* out, int rows, int T, int C,
+                        int vocab, void* stream);
+
+/* PNS judge front end: image NCHW fp16 in [-1, 1] (VAE output) -> area-averaged S x S -> [0, 1] -> CLIP mean / std
+ * normalisation -> patch rows [B*(S/P)^2, Kpad], k = c*P*P + py*P + px (flattened patch_embedding conv weight layout).
+ * mean3 / std3: HOST pointers to 3 floats. */
+int ih_resize_patchify_f16(const void* img_nchw, void* out, int B, int C, int Hin, int Win, int S, int P, int Kpad,
+                           const float* mean3, const float* std3, void* stream);
 
 /* General scheduler transition: the loop options the reference accepts beyond the default CFG path.
  *   use_cfg = 0 : guidance_scale <= 1 (custom_pipelines.py:223 do_classifier_free_guidance False): noise_pred and

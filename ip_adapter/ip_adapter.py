@@ -73,13 +73,19 @@ class IPAdapter:
         self.pipe = sd_pipe.to(device)
         self.set_ip_adapter()
 
-        # image encoder (CLIP ViT-bigG/14 with projection for SDXL): a [3P] transformers model, "next" row f2
+        # image encoder (CLIP ViT-bigG/14 with projection for SDXL, reference :81-84): the checkpoint folder is read with
+        # transformers, the tower itself runs on the native kernels (imagharmony_b200.clip.ClipVisionTower, row f2).
+        # `image_encoder_path` may also be a ready ClipVisionTower (tests: no weights exist offline).
         self.image_encoder = None
         self.clip_image_processor = None
-        if image_encoder_path is not None and os.path.isdir(str(image_encoder_path)):
-            from transformers import CLIPImageProcessor, CLIPVisionModelWithProjection
-            self.image_encoder = CLIPVisionModelWithProjection.from_pretrained(image_encoder_path).to(
-                self.device, dtype=torch.float16)
+        from imagharmony_b200.clip import ClipVisionTower
+        if isinstance(image_encoder_path, ClipVisionTower):
+            self.image_encoder = image_encoder_path
+        elif image_encoder_path is not None and os.path.isdir(str(image_encoder_path)):
+            from .encoders import load_image_encoder
+            self.image_encoder = load_image_encoder(image_encoder_path, self.device)
+        if self.image_encoder is not None:
+            from transformers import CLIPImageProcessor
             self.clip_image_processor = CLIPImageProcessor()
         self.number_class_crossattention = None
         if number_class_crossattention is not None:
@@ -160,7 +166,7 @@ class IPAdapter:
                 raise IHError("no CLIP image encoder loaded (image_encoder_path): pass clip_image_embeds=")
             images = [pil_image] if isinstance(pil_image, Image.Image) else list(pil_image)
             pixels = self.clip_image_processor(images=images, return_tensors="pt").pixel_values
-            emb = self.image_encoder(pixels.to(self.device, dtype=torch.float16)).image_embeds
+            emb = self.image_encoder(pixels).image_embeds
         emb = emb.to(self.device, dtype=torch.float16).contiguous()
         if extra_prompt_embeds is not None and self.number_class_crossattention is not None:      # :169-173
             aux = extra_prompt_embeds.to(self.device, torch.float16)
@@ -231,7 +237,6 @@ class IPAdapterPlusXL(IPAdapter):
                 raise IHError("no CLIP image encoder loaded: pass clip_hidden_states= / uncond_clip_hidden_states=")
             images = [pil_image] if isinstance(pil_image, Image.Image) else list(pil_image)
             pixels = self.clip_image_processor(images=images, return_tensors="pt").pixel_values
-            pixels = pixels.to(self.device, dtype=torch.float16)
 
             def penultimate(x):
                 return self.image_encoder(x, output_hidden_states=True).hidden_states[-2]

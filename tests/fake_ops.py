@@ -31,7 +31,7 @@ def fold_layernorm(w, bias, gamma, beta):
 
 
 def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, gelu=False,
-           out=None, tile_n=0, ln=None, stats_out=None):
+           out=None, tile_n=0, ln=None, stats_out=None, quick_gelu=False):
     _count[0] += 1
     y = x.float() @ w.float().t()
     if ln is not None:
@@ -52,6 +52,8 @@ def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, ge
         y = F.silu(y)
     if gelu:
         y = F.gelu(y)
+    if quick_gelu:
+        y = y * torch.sigmoid(1.702 * y)
     if residual is not None:
         y = y + residual.float()
     y = y.to(x.dtype)
@@ -259,3 +261,31 @@ def im2col3x3_nchw(x_nchw, kpad=64, out=None):
 def nhwc_to_nchw(x, C, out=None):
     _count[0] += 1
     return x[..., :C].permute(0, 3, 1, 2).contiguous()
+
+
+def attention_generic(q, k, v, B, H, Nq, Nk, dqk, dv, scale, causal=False, out=None):
+    _count[0] += 1
+    qh = q[:, :H * dqk].float().reshape(B, Nq, H, dqk).permute(0, 2, 1, 3)
+    kh = k[:, :H * dqk].float().reshape(B, Nk, H, dqk).permute(0, 2, 1, 3)
+    vh = v[:, :H * dv].float().reshape(B, Nk, H, dv).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        mask = torch.ones(Nq, Nk, dtype=torch.bool).tril(Nk - Nq)
+        s = s.masked_fill(~mask, float("-inf"))
+    o = (s.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B * Nq, H * dv).to(q.dtype)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
+
+
+def embed_tokens(ids, tok_emb, pos_emb, out=None):
+    _count[0] += 1
+    B, T = ids.shape
+    return (tok_emb[ids.long()] + pos_emb[:T][None]).reshape(B * T, -1)
+
+
+def resize_patchify(img, size, patch, kpad, mean, std, out=None):
+    _count[0] += 1
+    from oracle.clip_ref import resize_patchify_ref
+    return resize_patchify_ref(img.float(), size, patch, kpad, mean, std).to(img.dtype)

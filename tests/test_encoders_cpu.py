@@ -1,5 +1,5 @@
-"""Prompt conditioning (scope row f2): ClipPromptEncoder restates diffusers' SDXL encode_prompt on top of the transformers
-CLIP classes.  No weights / vocabularies exist offline, so the test builds miniature random CLIP text models and a toy
+"""Prompt conditioning (scope row f2): ClipPromptEncoder restates diffusers' SDXL encode_prompt on top of the NATIVE CLIP text
+towers (imagharmony_b200.clip), checked against the transformers CLIP classes.  No weights / vocabularies exist offline, so the test builds miniature random CLIP text models and a toy
 character-level CLIP vocabulary."""
 import json
 
@@ -23,7 +23,20 @@ def _toy_tokenizer(tmp_path, name):
     return CLIPTokenizer(str(d / "vocab.json"), str(d / "merges.txt"), model_max_length=77), len(vocab)
 
 
-def test_clip_prompt_encoder_semantics(tmp_path):
+@pytest.fixture()
+def patched(monkeypatch):
+    """The native CLIP towers on the CPU stand-in ops (fp32); the kernels are exercised by tests/test_clip_gpu.py."""
+    import fake_ops
+    import imagharmony_b200.clip as clip
+    import imagharmony_b200.ops as real_ops
+    for name in dir(fake_ops):
+        if not name.startswith("_") and callable(getattr(fake_ops, name)) and hasattr(real_ops, name):
+            monkeypatch.setattr(real_ops, name, getattr(fake_ops, name))
+    monkeypatch.setattr(clip, "_DTYPE", [torch.float32])
+    yield
+
+
+def test_clip_prompt_encoder_semantics(tmp_path, patched):
     transformers = pytest.importorskip("transformers")
     from transformers import CLIPTextConfig, CLIPTextModel, CLIPTextModelWithProjection
     from ip_adapter.encoders import ClipPromptEncoder

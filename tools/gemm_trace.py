@@ -37,6 +37,8 @@ def run(label, M, N, K, geglu=False, tn=0):
 
 run("1 tile 128x256x64      ", 128, 256, 64, tn=256)
 run("1280^2 (80 tiles)      ", 2048, 1280, 1280, tn=256)
+run("1280^2 auto (112 tiles) ", 2048, 1280, 1280, tn=0)
+run("1280^2 bn128 (160 tiles)", 2048, 1280, 1280, tn=128)
 run("QKV 2048x3840x1280     ", 2048, 3840, 1280, tn=256)
 run("FF-in geglu            ", 2048, 10240, 1280, geglu=True, tn=256)
 run("FF-out 2048x1280x5120  ", 2048, 1280, 5120, tn=256)
