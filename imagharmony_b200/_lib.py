@@ -66,6 +66,10 @@ SIGNATURES = {
     "ih_gemm_ln_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p,
                                c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                c_float, c_void_p, c_void_p]),
+    "ih_gemm_scaled_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong,
+                                   c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ih_conv2d_scaled_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, c_void_p]),
     "ih_gemm_set_trace": (None, [c_void_p]),
     "ih_conv2d_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -79,6 +83,7 @@ SIGNATURES = {
                                      c_int, c_float, c_int, c_void_p]),
     "ih_attention_workspace_bytes": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
     "ih_softmax_rows_f16": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_void_p]),
+    "ih_softmax_rows_masked_f16": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "ih_attention_set_split_policy": (None, [c_int]),
     "ih_attention_set_trace": (None, [c_void_p]),
     "ih_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -12,6 +12,7 @@
 // PV MMA yields  softmax(q k_t^T) v_t + ip_scale * softmax(q k_ip^T) v_ip  -- attention_processor.py:423-450.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "../../include/ih_api.h"
@@ -38,6 +39,8 @@ struct AttnParams {
   int H, qpairs, n_whole, split;
   float* ws_o;   // [slots][256][64]
   float* ws_ml;  // [slots][256][2]
+  int* ws_cnt;   // [split pairs] arrival counters (zero between launches) for the in-kernel merge; nullptr = separate
+                 // attn_combine_kernel launch
   long long* trace;  // optional clock64 stamps of CTA 0, KV blocks 4..7 (ih_attention_set_trace); nullptr in production
 };
 
@@ -560,10 +563,11 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int pair = blockIdx.x, jb = 0, je = p.num_kv_blocks, slot = -1;
+  int pair = blockIdx.x, jb = 0, je = p.num_kv_blocks, slot = -1, sp = 0;
   if (pair >= p.n_whole) {
     slot = pair - p.n_whole;
-    const int sp = slot / p.split, part = slot - sp * p.split;
+    sp = slot / p.split;
+    const int part = slot - sp * p.split;
     pair = p.n_whole + sp;
     jb = part * p.num_kv_blocks / p.split;          // balanced contiguous partition of the KV blocks
     je = (part + 1) * p.num_kv_blocks / p.split;
@@ -849,6 +853,60 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_f16_kernel(const __grid_c
           tma_store_commit();
           tma_store_wait_all();
         }
+        if (p.ws_cnt) {
+          // In-kernel merge: the LAST of the `split` parts of this query pair to arrive (device-scope counter) combines
+          // all partials -- in part order, so the result does not depend on who arrives last -- and writes the
+          // output rows; no second launch.  M = max_i m_i, out = sum_i O_i 2^(m_i - M) / sum_i l_i 2^(m_i - M).
+          volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 2);
+          const int nsoft = tileB_active ? 512 : 256;
+          __threadfence();                       // my (m, l) row / the elected thread's completed bulk store
+          named_bar_sync(11, nsoft);
+          if (idx == 0 && lane == 0) {
+            __threadfence();
+            const int old = atomicAdd(&p.ws_cnt[sp], 1);
+            const int last = (old == p.split - 1) ? 1 : 0;
+            if (last) p.ws_cnt[sp] = 0;          // ready for the next launch
+            *last_flag = last;
+          }
+          named_bar_sync(11, nsoft);
+          if (*last_flag && qrow < p.Nq) {
+            __threadfence();
+            const int row = t * 128 + r;
+            const float2* ml = reinterpret_cast<const float2*>(p.ws_ml);
+            float mmax = -INFINITY;
+            for (int i = 0; i < p.split; ++i) mmax = fmaxf(mmax, __ldcg(&ml[((long long)sp * p.split + i) * 256 + row]).x);
+            float acc[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+            float l = 0.f;
+            for (int i = 0; i < p.split; ++i) {
+              const long long wrow = ((long long)sp * p.split + i) * 256 + row;
+              const float2 v = __ldcg(&ml[wrow]);
+              const float w = ex2f(v.x - mmax);
+              l = fmaf(v.y, w, l);
+              const float4* src = reinterpret_cast<const float4*>(p.ws_o + wrow * 64);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 o = __ldcg(&src[(hh * 8 + g) ^ (r & 15)]);   // chunk permutation of the staging above
+                acc[g * 4 + 0] = fmaf(o.x, w, acc[g * 4 + 0]);
+                acc[g * 4 + 1] = fmaf(o.y, w, acc[g * 4 + 1]);
+                acc[g * 4 + 2] = fmaf(o.z, w, acc[g * 4 + 2]);
+                acc[g * 4 + 3] = fmaf(o.w, w, acc[g * 4 + 3]);
+              }
+            }
+            const float inv = 1.f / l;
+            __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64 + hh * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_half2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv);
+              o.y = pack_half2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv);
+              o.z = pack_half2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv);
+              o.w = pack_half2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv);
+              *reinterpret_cast<uint4*>(dst + g * 8) = o;
+            }
+          }
+        }
       } else if (qrow < p.Nq) {
         const float inv = 1.f / l_tot;
         __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64 + hh * 32;
@@ -954,7 +1012,10 @@ extern "C" long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, 
   int n_whole, split;
   const int pairs = B * H * ((Nq + 255) / 256);
   attn2_plan(pairs, (Nk + 127) / 128, &n_whole, &split);
-  return (long long)(pairs - n_whole) * split * 256 * (64 + 2) * (long long)sizeof(float);
+  // partial O rows + (m, l) per part, then one arrival counter per split pair (the caller provides ZEROED memory; the
+  // kernel leaves the counters at zero)
+  return (long long)(pairs - n_whole) * split * 256 * (64 + 2) * (long long)sizeof(float) +
+         (long long)(pairs - n_whole) * (long long)sizeof(int);
 }
 
 extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
@@ -1040,16 +1101,23 @@ extern "C" int ih_attention_ws_f16(const void* q, long long ldq, const void* k, 
     const int pairs = B * H * p.qpairs;
     attn2_plan(pairs, p.num_kv_blocks, &p.n_whole, &p.split);
     const long long slots = (long long)(pairs - p.n_whole) * p.split;
-    if (slots > 0 && (!workspace || workspace_bytes < slots * 256 * 66 * (long long)sizeof(float))) {
+    const long long need = slots * 256 * 66 * (long long)sizeof(float) + (long long)(pairs - p.n_whole) * (long long)sizeof(int);
+    if (slots > 0 && (!workspace || workspace_bytes < need)) {
       p.n_whole = pairs;   // no (or too small a) workspace: every pair runs whole
       p.split = 1;
     }
     const int n_split_ctas = (pairs - p.n_whole) * p.split;
     p.ws_o = (float*)workspace;
     p.ws_ml = p.ws_o + (long long)n_split_ctas * 256 * 64;
+    // IH_ATTN_FUSED_MERGE=0: merge the parts with a second launch (attn_combine_kernel) instead of in-kernel
+    static const bool fused_merge = [] {
+      const char* e = getenv("IH_ATTN_FUSED_MERGE");
+      return !(e && e[0] == '0');
+    }();
+    p.ws_cnt = (fused_merge && n_split_ctas > 0) ? reinterpret_cast<int*>(p.ws_ml + (long long)n_split_ctas * 256 * 2) : nullptr;
     IH_CUDA(launch_kernel(attn2_f16_kernel, dim3(p.n_whole + n_split_ctas), dim3(A2_THREADS), (size_t)(A2_SMEM_BYTES),
                           (cudaStream_t)stream, tq, tk, tv, p));
-    if (n_split_ctas > 0)
+    if (n_split_ctas > 0 && !p.ws_cnt)
       IH_CUDA(launch_kernel(attn_combine_kernel, dim3((pairs - p.n_whole) * 4), dim3(256), (size_t)0,
                             (cudaStream_t)stream, p));
     return 0;

@@ -59,6 +59,7 @@ struct GemmParams {
   // Wc[n,k] = W[n,k] gamma[k] - mean_k(W[n,:] gamma) -- so x Wc^T = (x - mean(x)) (W gamma)^T -- and applies
   //   out = rstd[m] * acc + c[n],  c = W beta + b (passed as `bias`)   (= LayerNorm(x) W^T + b in real arithmetic)
   // with rstd rebuilt from the producer's slabs (ln_stats [ln_slabs, M, 2]).
+  float alpha;   // out = alpha * acc (* rstd) + bias ...: power-of-two output scaling of the VAE's scaled residual stream
   float* stats_out;
   const float* ln_stats;
   int ln_slabs;
@@ -72,9 +73,19 @@ struct GemmSmem {
   static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = 2 * BM * 64 * 2;  // two 128-row x 64-column fp16 epilogue staging slabs (TMA store)
+  static constexpr int BN_OUT = GEGLU ? BN / 2 : BN;
+  static constexpr int SLABS = (BN_OUT + 63) / 64;   // 64-column output slabs per tile
+  static constexpr int SLAB_BYTES = BM * 64 * 2;     // one 128-row x 64-column fp16 staging slab (TMA store source)
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = TILE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int BIAS_BYTES = (BN + BN_OUT) * 2;  // bias row of the tile (GEGLU: value | gate) + uniform row-bias row
+  static constexpr int SMEM_LIMIT = 232448;             // 227 KiB per CTA
+  // one staging slab per output slab when that fits (no buffer reuse inside a tile), else two (ping-pong)
+  static constexpr int STG_SLABS =
+      (TILE_BYTES + SLABS * SLAB_BYTES + BAR_BYTES + BIAS_BYTES + 1024 <= SMEM_LIMIT) ? SLABS : (SLABS < 2 ? SLABS : 2);
+  static constexpr int STG_BYTES = STG_SLABS * SLAB_BYTES;
+  static constexpr int BIAS_OFF = TILE_BYTES + STG_BYTES + BAR_BYTES;
+  static constexpr int TOTAL = TILE_BYTES + STG_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
+  static_assert(TOTAL <= SMEM_LIMIT, "GEMM shared-memory budget exceeded");
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
@@ -97,13 +108,13 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
   using S = GemmSmem<BN, STAGES, GEGLU, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + S::TILE_BYTES;            // [2] epilogue staging slabs, 16 KiB each (1024-aligned)
+  uint8_t* stg = smem + S::TILE_BYTES;            // [STG_SLABS] epilogue staging slabs, 16 KiB each (1024-aligned)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;         // [2] residual slab landed (one per epilogue half-group)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [4] residual slab landed (one per staging slab)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,8 +144,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       mbar_init(&empty_bar[s], 1);
     }
     tma_prefetch_desc(&omap);
+    for (int a = 0; a < 4; ++a) mbar_init(&res_bar[a], 1);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&res_bar[a], 1);
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * (PAIR ? 2 : 1));
     }
@@ -266,20 +277,30 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (8 warps = two half-groups of 128 rows) ------------------------
-    // Each half-group drains every other 64-column slab of the accumulator: TMEM -> registers (one row per thread)
-    // -> bias / activation / GEGLU / residual -> fp16 row segment (128 B) into a 128B-swizzled staging slab ->
-    // one TMA store per slab (fully coalesced, clipped at the M / N / image edges by the tensor map).  The residual
-    // slab is TMA-loaded into the same staging buffer first and updated in place.
+    // ------------------------------ epilogue (8 warps, 256 threads) -------------------------------------------------
+    // Latency-oriented: at UNet batch 2 most launches hold ONE tile per CTA, so the epilogue is fully exposed (trace:
+    // main loop 5.6 us, old epilogue 4.6 us for a 128x192 tile against a TMEM-read floor of 0.8 us).  Therefore
+    //   * the bias row of the tile (GEGLU: value | gate) and a tile-uniform row-bias row are staged in shared memory
+    //     BEFORE the accumulator is ready (no dependent global loads between TMEM and the store);
+    //   * every 64-column slab is drained by ALL 8 warps (warp quarter q = TMEM lanes, column half = warps 0-3 / 4-7:
+    //     32 columns each), so the critical path is SLABS short steps instead of ceil(SLABS / 2) long ones;
+    //   * each slab has its own staging buffer when shared memory allows (BN <= 192), else two ping-pong buffers; one
+    //     thread issues all TMA loads (residual) / stores, stores are never waited for inside a tile unless a buffer
+    //     is reused; residual slabs are prefetched behind the main loop.
+    // TMEM -> registers (one row per thread) -> bias / LN-fold / activation / GEGLU / residual -> fp16 row segment into
+    // the 128B-swizzled staging slab -> TMA store (clipped at the M / N / image edges by the tensor map).
+    const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;     // half-group: owns staging slab `half`
-    const int r = q * 32 + lane;
-    const bool elected = (q == 0 && lane == 0);
-    uint8_t* my_stg = stg + half * (BM * 128);
-    uint8_t* my_row = my_stg + r * 128;
+    const int half = ew >> 2;             // which 32 of the 64 columns of every slab
+    const int r = q * 32 + lane;          // accumulator row
+    const int etid = ew * 32 + lane;      // 0..255
+    const bool issuer = (ew == 0 && lane == 0);
     const int rx = r & 7;
-    constexpr int SLABS = (BN_OUT + 63) / 64;
-    uint32_t res_phase = 0;
+    constexpr int SLABS = S::SLABS;
+    constexpr int NBUF = S::STG_SLABS;
+    __half* sBias = reinterpret_cast<__half*>(smem + S::BIAS_OFF);   // [BN]: columns of this tile (GEGLU: value | gate)
+    __half* sRowb = sBias + BN;                                       // [BN_OUT]: row-bias row when uniform over the tile
+    uint32_t res_par = 0;                 // bit b: parity of res_bar[b]
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int n_tile = tile % n_tiles;
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       const uint32_t acc_phase = (it >> 1) & 1;
       long long orow;
       int img = 0, x0 = 0, y0 = 0;
-      bool tile_live = m_tile < p.m_tiles;
+      const bool tile_live = m_tile < p.m_tiles;
       if (p.mode == 0) {
         orow = (long long)m_tile * BM + r;
       } else {
@@ -305,22 +326,46 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         orow = ((long long)img * p.Ho + y) * p.Wo + x;
       }
       const __half* rb = nullptr;
+      bool rb_uniform = false;
       if (p.rowbias && tile_live) {
-        long long grp = orow / p.rows_per_group;
         const long long max_grp = ((long long)p.M - 1) / p.rows_per_group;
+        long long grp = orow / p.rows_per_group;
         if (grp > max_grp) grp = max_grp;
         rb = p.rowbias + grp * p.ld_rowbias;
+        if (p.mode == 1) {
+          rb_uniform = true;   // a conv tile never leaves its image, rows_per_group = Ho * Wo
+        } else {
+          long long g0 = ((long long)m_tile * BM) / p.rows_per_group, g1 = ((long long)m_tile * BM + BM - 1) / p.rows_per_group;
+          if (g1 > max_grp) g1 = max_grp;
+          rb_uniform = (g0 == g1);
+        }
       }
-
-      // the residual tile of this half-group's first slab is fetched now, behind the main loop (the staging slab is
-      // free: the previous tile's store has been read out); later slabs must wait for their predecessor's store
-      if (tile_live && p.residual && half < SLABS && n0 + half * 64 < p.N && elected) {
-        mbar_arrive_expect_tx(&res_bar[half], BM * 128);
-        if (p.mode == 0) tma_load_2d(my_stg, &rmap, &res_bar[half], n0 + half * 64, m_tile * BM);
-        else tma_load_4d(my_stg, &rmap, &res_bar[half], n0 + half * 64, x0, y0, img);
+      // (a) bias rows of this tile -> shared memory (hidden behind the main loop)
+      if (tile_live) {
+        for (int c = etid; c < BN; c += GEMM_EPI_WARPS * 32) {
+          const int lc = GEGLU ? (c < BN / 2 ? c : c - BN / 2) : c;            // tile-local output column
+          const int wc = GEGLU ? (c < BN / 2 ? n0 + c : p.gate_row_off + n0 + lc) : n0 + c;   // row of W / entry of bias
+          sBias[c] = (p.bias && n0 + lc < p.N) ? p.bias[wc] : __float2half_rn(0.f);
+        }
+        if (rb_uniform)
+          for (int c = etid; c < BN_OUT; c += GEMM_EPI_WARPS * 32) sRowb[c] = (n0 + c < p.N) ? rb[n0 + c] : __float2half_rn(0.f);
       }
-      float ln_rstd = 1.f;
-      if (p.ln_stats && tile_live && orow < p.M) {   // hidden behind the main loop of this tile
+      // all epilogue threads: bias rows visible; the issuer has waited for the previous tile's stores (end of loop body),
+      // so every staging buffer is free from here on
+      named_bar_sync(1, GEMM_EPI_WARPS * 32);
+      // (b) residual slabs of the first NBUF slabs are fetched now, behind the main loop
+      if (issuer && tile_live && p.residual) {
+        for (int sl = 0; sl < SLABS && sl < NBUF; ++sl) {
+          const int col0 = n0 + sl * 64;
+          if (col0 >= p.N) break;
+          mbar_arrive_expect_tx(&res_bar[sl], BM * 128);
+          if (p.mode == 0) tma_load_2d(stg + sl * S::SLAB_BYTES, &rmap, &res_bar[sl], col0, m_tile * BM);
+          else tma_load_4d(stg + sl * S::SLAB_BYTES, &rmap, &res_bar[sl], col0, x0, y0, img);
+        }
+      }
+      // (c) folded LayerNorm: 1 / std of my row from the producer's slabs (hidden behind the main loop of this tile)
+      float ln_rstd = p.alpha;
+      if (p.ln_stats && tile_live && orow < p.M) {
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + orow;   // [slab][row]: coalesced over rows
         float ssum = 0.f, ssq = 0.f;
         for (int i0 = 0; i0 < p.ln_slabs; i0 += 10) {   // 10 independent loads in flight: one L2 round trip per 640 features
@@ -336,165 +381,161 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         }
         const float ln_mean = ssum * p.ln_inv_c;
         const float var = fmaxf(ssq * p.ln_inv_c - ln_mean * ln_mean, 0.f);
-        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_rstd = p.alpha * rsqrtf(var + p.ln_eps);
       }
 
+      // (d) the accumulator
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       if (threadIdx.x == 64) stamp(4 + (it < 3 ? it : 3));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
 
       int last_slab = -1;
-      for (int sl = half; sl < SLABS; sl += 2)
-        if (n0 + sl * 64 < p.N) last_slab = sl;
+      if (tile_live)
+        for (int sl = 0; sl < SLABS; ++sl)
+          if (n0 + sl * 64 < p.N) last_slab = sl;
       bool arrived = false;
 #pragma unroll 1
-      for (int sl = half; sl < SLABS; sl += 2) {
+      for (int sl = 0; sl <= last_slab; ++sl) {
         const int col0 = n0 + sl * 64;
-        const bool live = tile_live && (col0 < p.N);   // uniform over the half-group
-        if (live && p.residual && sl != half) {
-          if (elected) {
-            mbar_arrive_expect_tx(&res_bar[half], BM * 128);
-            if (p.mode == 0) tma_load_2d(my_stg, &rmap, &res_bar[half], col0, m_tile * BM);
-            else tma_load_4d(my_stg, &rmap, &res_bar[half], col0, x0, y0, img);
-          }
-        }
-        if (live && p.residual) {
-          mbar_wait(&res_bar[half], res_phase);
-          res_phase ^= 1;
-        }
-        float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
-        for (int h32 = 0; h32 < 2; ++h32) {
-          uint32_t v[32];
-          uint32_t g[32];
-          // bias / gate-bias / row-bias vectors of 8 columns, fetched one j-step ahead of their use so that their L1 / L2
-          // latency overlaps the TMEM load (first step) or the arithmetic of the previous step.  Columns past N are
-          // clipped by the TMA store, so a clamped (in-range) address is good enough for them.
-          auto fetch = [&](int j, uint4& bv, uint4& gv, uint4& rv) {
-            int col = col0 + j * 8;
-            if (col > p.N - 8) col = p.N - 8;
-            bv = gv = rv = make_uint4(0u, 0u, 0u, 0u);
-            if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-            if (GEGLU && p.bias) gv = __ldg(reinterpret_cast<const uint4*>(p.bias + p.gate_row_off + col));
-            if (rb) rv = __ldg(reinterpret_cast<const uint4*>(rb + col));
-          };
-          uint4 bv, gv, rv;
-          if (live) {
-            tmem_ld_32x32b_x32(taddr + sl * 64 + h32 * 32, v);
-            if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64 + h32 * 32, g);
-            fetch(h32 * 4, bv, gv, rv);
-            tmem_ld_wait();
-          }
-          if (sl == last_slab && h32 == 1) {
-            // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
-            arrived = true;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
-              else mbar_arrive(&tmem_empty_bar[acc]);
+        const int buf = sl % NBUF;
+        uint8_t* sbuf = stg + buf * S::SLAB_BYTES;
+        uint8_t* my_row = sbuf + r * 128;
+        uint32_t v[32];
+        uint32_t g[32];
+        tmem_ld_32x32b_x32(taddr + sl * 64, v);
+        if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g);
+        if (sl >= NBUF) {
+          // staging-buffer reuse (BN = 256 only): the store of slab sl - NBUF must have read the buffer out; then the
+          // residual slab is fetched into it
+          if (issuer) {
+            tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
+            if (p.residual) {
+              mbar_arrive_expect_tx(&res_bar[buf], BM * 128);
+              if (p.mode == 0) tma_load_2d(sbuf, &rmap, &res_bar[buf], col0, m_tile * BM);
+              else tma_load_4d(sbuf, &rmap, &res_bar[buf], col0, x0, y0, img);
             }
           }
-          if (live) {
+          named_bar_sync(2, GEMM_EPI_WARPS * 32);
+        }
+        tmem_ld_wait();
+        if (sl == last_slab) {
+          // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
+          arrived = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+        if (p.residual) {
+          mbar_wait(&res_bar[buf], (res_par >> buf) & 1u);
+          res_par ^= 1u << buf;
+        }
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const int j = h32 * 4 + j4;
-              const bool col_ok = col0 + j * 8 < p.N;
-              uint4 nbv, ngv, nrv;
-              if (j4 < 3) fetch(j + 1, nbv, ngv, nrv);
-              float x[8];
-              {
-                // acc * rstd + bias: rstd = 1 without a folded LayerNorm; with one, `bias` carries W beta + b and the
-                // weight rows are gamma-scaled AND centred, so the mean term has already cancelled inside the MMA
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int j = half * 4 + j4;             // 16-byte chunk of the 64-column slab row
+          const int lc = sl * 64 + j * 8;          // tile-local output column of the chunk
+          float x[8];
+          {
+            // acc * rstd + bias: rstd = alpha without a folded LayerNorm; with one, `bias` carries W beta + b and the
+            // weight rows are gamma-scaled AND centred, so the mean term has already cancelled inside the MMA
+            const uint4 bv = *reinterpret_cast<const uint4*>(sBias + lc);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_half2(bw[e]);
-                  x[2 * e] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e]), f.x);
-                  x[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e + 1]), f.y);
-                }
-              }
-              if (GEGLU) {
-                float gt[8];
-                const uint32_t bw[4] = {gv.x, gv.y, gv.z, gv.w};
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_half2(bw[e]);
+              x[2 * e] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e]), f.x);
+              x[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(v[j4 * 8 + 2 * e + 1]), f.y);
+            }
+          }
+          if (GEGLU) {
+            float gt[8];
+            const uint4 gv = *reinterpret_cast<const uint4*>(sBias + BN / 2 + lc);
+            const uint32_t bw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_half2(bw[e]);
-                  gt[2 * e] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e]), f.x);
-                  gt[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e + 1]), f.y);
-                }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_half2(bw[e]);
+              gt[2 * e] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e]), f.x);
+              gt[2 * e + 1] = fmaf(ln_rstd, __uint_as_float(g[j4 * 8 + 2 * e + 1]), f.y);
+            }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
-              }
-              {
-                const uint32_t bw[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int e = 0; e < 8; ++e) x[e] *= gelu_erf_f(gt[e]);
+          }
+          if (rb) {
+            uint4 rv;
+            if (rb_uniform) {
+              rv = *reinterpret_cast<const uint4*>(sRowb + lc);
+            } else {   // rows of several groups in one tile (not used by the UNet): per-row global loads
+              int col = n0 + lc;
+              if (col > p.N - 8) col = p.N - 8;
+              rv = __ldg(reinterpret_cast<const uint4*>(rb + col));
+            }
+            const uint32_t bw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_half2(bw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-              }
-              if (j4 < 3) {
-                bv = nbv;
-                gv = ngv;
-                rv = nrv;
-              }
-              if (p.act == 1) {
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_half2(bw[e]);
+              x[2 * e] += f.x;
+              x[2 * e + 1] += f.y;
+            }
+          }
+          if (p.act == 1) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
-              } else if (p.act == 2) {
+            for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
+          } else if (p.act == 2) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
-              } else if (p.act == 3) {   // quick_gelu x * sigmoid(1.702 x) ([3P] CLIP-L text tower MLP)
+            for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
+          } else if (p.act == 3) {   // quick_gelu x * sigmoid(1.702 x) ([3P] CLIP-L text tower MLP)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = __fdividef(x[e], 1.f + __expf(-1.702f * x[e]));
-              }
-              uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ rx) << 4));
-              if (p.residual) {
-                const uint4 b4 = *slot;
-                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int e = 0; e < 8; ++e) x[e] = __fdividef(x[e], 1.f + __expf(-1.702f * x[e]));
+          }
+          uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ rx) << 4));
+          if (p.residual) {
+            const uint4 b4 = *slot;
+            const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_half2(bw[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-              }
-              uint4 o;
-              o.x = pack_half2(x[0], x[1]);
-              o.y = pack_half2(x[2], x[3]);
-              o.z = pack_half2(x[4], x[5]);
-              o.w = pack_half2(x[6], x[7]);
-              *slot = o;
-              if (p.stats_out && col_ok) {   // statistics of exactly the fp16 values a later LayerNorm would read
-                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_half2(bw[e]);
+              x[2 * e] += f.x;
+              x[2 * e + 1] += f.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_half2(x[0], x[1]);
+          o.y = pack_half2(x[2], x[3]);
+          o.z = pack_half2(x[4], x[5]);
+          o.w = pack_half2(x[6], x[7]);
+          *slot = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, GEMM_EPI_WARPS * 32);        // the slab is complete in shared memory
+        if (issuer) {
+          if (p.mode == 0) tma_store_2d(&omap, sbuf, col0, m_tile * BM);
+          else tma_store_4d(&omap, sbuf, col0, x0, y0, img);
+          tma_store_commit();
+        }
+        if (p.stats_out && half == (sl & 1) && orow < p.M) {
+          // row statistics of exactly the fp16 values a later LayerNorm would read: my whole 64-column row of the slab
+          // (both column halves), re-read from the staging buffer; one writer per (slab, row) slot
+          float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_half2(ow[e]);
-                  st_sum += f.x + f.y;
-                  st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
-                }
+          for (int c = 0; c < 8; ++c) {
+            if (col0 + c * 8 < p.N) {
+              const uint4 o = *reinterpret_cast<const uint4*>(my_row + ((c ^ rx) << 4));
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_half2(ow[e]);
+                st_sum += f.x + f.y;
+                st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
               }
             }
           }
-        }
-        if (live && p.stats_out && orow < p.M)
           reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
-        if (live) {
-          fence_proxy_async_smem();
-          named_bar_sync(1 + half, 128);
-          if (elected) {
-            if (p.mode == 0) tma_store_2d(&omap, my_stg, col0, m_tile * BM);
-            else tma_store_4d(&omap, my_stg, col0, x0, y0, img);
-            tma_store_commit();
-            tma_store_wait_read0();   // the staging slab may be overwritten once the store has read it
-          }
-          named_bar_sync(1 + half, 128);
         }
       }
-      if (!arrived) {   // this half-group had no live slab in the tile (narrow N, dead half tile): still release
+      if (!arrived) {   // no live slab in the tile (dead half tile of a CTA pair): still release the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -502,10 +543,10 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           else mbar_arrive(&tmem_empty_bar[acc]);
         }
       }
+      // the staging buffers may be rewritten (next tile) / must stay valid (kernel end) until the bulk stores have read
+      // them; global visibility is given by kernel completion (the next kernel's griddepcontrol.wait / stream order)
+      if (issuer) tma_store_wait_read0();
     }
-    // shared memory must stay valid until the last bulk store has read it; global visibility is given by kernel
-    // completion (the next kernel's griddepcontrol.wait / stream order)
-    if (elected) tma_store_wait_read0();
   }
 
   tc_fence_before();
@@ -637,17 +678,37 @@ using namespace ih;
 // 0..3+, 8 CTA done); pass NULL to disable.
 extern "C" void ih_gemm_set_trace(void* device_buffer) { ih::g_trace = (unsigned long long*)device_buffer; }
 
+static int gemm_impl(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
+                     int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
+                     long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats,
+                     int ln_slabs, float ln_eps, void* stats_out, float alpha, void* stream);
+
 extern "C" int ih_gemm_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                            int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                            long long ldo, int M, int N, int K, int epilogue, int tile_n, void* stream) {
-  return ih_gemm_ln_f16(a, lda, w, bias, rowbias, rows_per_group, ld_rowbias, residual, ldr, out, ldo, M, N, K, epilogue,
-                        tile_n, nullptr, 0, 0.f, nullptr, stream);
+  return gemm_impl(a, lda, w, bias, rowbias, rows_per_group, ld_rowbias, residual, ldr, out, ldo, M, N, K, epilogue,
+                   tile_n, nullptr, 0, 0.f, nullptr, 1.f, stream);
+}
+
+extern "C" int ih_gemm_scaled_f16(const void* a, long long lda, const void* w, const void* bias, const void* residual,
+                                  long long ldr, void* out, long long ldo, int M, int N, int K, int epilogue, float alpha,
+                                  void* stream) {
+  return gemm_impl(a, lda, w, bias, nullptr, 0, 0, residual, ldr, out, ldo, M, N, K, epilogue, 0, nullptr, 0, 0.f,
+                   nullptr, alpha, stream);
 }
 
 extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                               int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                               long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats,
                               int ln_slabs, float ln_eps, void* stats_out, void* stream) {
+  return gemm_impl(a, lda, w, bias, rowbias, rows_per_group, ld_rowbias, residual, ldr, out, ldo, M, N, K, epilogue,
+                   tile_n, ln_stats, ln_slabs, ln_eps, stats_out, 1.f, stream);
+}
+
+static int gemm_impl(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
+                     int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
+                     long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats,
+                     int ln_slabs, float ln_eps, void* stats_out, float alpha, void* stream) {
   IH_CHECK(a && w && out, IH_ERR_ARG, "ih_gemm_f16: null pointer");
   IH_CHECK(M > 0 && N > 0 && K > 0, IH_ERR_SHAPE, "ih_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
   IH_CHECK(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, IH_ERR_ALIGN,
@@ -689,6 +750,7 @@ extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const
   p.ln_slabs = ln_slabs;
   p.ln_inv_c = 1.0f / (float)K;
   p.ln_eps = ln_eps;
+  p.alpha = alpha;
   const int m_tiles = (M + BM - 1) / BM;
   CUtensorMap omap, rmap;
   {
@@ -707,9 +769,25 @@ extern "C" int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const
   return dispatch(amaps, omap, rmap, w, N, K, p, m_tiles, geglu, tile_n, (cudaStream_t)stream);
 }
 
+static int conv_impl(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
+                     const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
+                     int tile_n, float alpha, void* stream);
+
 extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias,
                              long long ld_rowbias, const void* residual, void* out, int B, int Hin, int Win, int Cin,
                              int Cout, int ksize, int stride, int tile_n, void* stream) {
+  return conv_impl(x, w, bias, rowbias, ld_rowbias, residual, out, B, Hin, Win, Cin, Cout, ksize, stride, tile_n, 1.f,
+                   stream);
+}
+
+extern "C" int ih_conv2d_scaled_f16(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                                    int B, int Hin, int Win, int Cin, int Cout, int stride, float alpha, void* stream) {
+  return conv_impl(x, w, bias, nullptr, 0, residual, out, B, Hin, Win, Cin, Cout, 3, stride, 0, alpha, stream);
+}
+
+static int conv_impl(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
+                     const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
+                     int tile_n, float alpha, void* stream) {
   IH_CHECK(x && w && out, IH_ERR_ARG, "ih_conv2d_f16: null pointer");
   IH_CHECK(ksize == 3, IH_ERR_ARG, "ih_conv2d_f16: ksize must be 3 (1x1 convs are ih_gemm_f16)");
   IH_CHECK(stride == 1 || stride == 2, IH_ERR_ARG, "ih_conv2d_f16: stride must be 1 or 2");
@@ -749,6 +827,7 @@ extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, con
   p.out = (__half*)out;
   p.ldo = Cout;
   p.trace = g_trace;
+  p.alpha = alpha;
 
   TmapSet4 amaps;
   const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, 1u};

@@ -593,7 +593,8 @@ __global__ void mean_tokens_kernel(const __half* __restrict__ x, __half* __restr
 // of the VAE decoder's mid block (scores = (q / sqrt(d)) k^T from the tensor-core GEMM).
 constexpr int SMX_THREADS = 256;
 constexpr int SMX_MAXV = 16;
-__global__ void __launch_bounds__(SMX_THREADS) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols) {
+__global__ void __launch_bounds__(SMX_THREADS) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols,
+                                                                   int valid) {
   __shared__ float s_red[SMX_THREADS / 32];
   __shared__ float s_bcast;
   pdl_launch_dependents();
@@ -608,7 +609,10 @@ __global__ void __launch_bounds__(SMX_THREADS) softmax_rows_kernel(__half* __res
     if (vi < nv) {
       ld8(row + vi * 8, v[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[i][e]);
+      for (int e = 0; e < 8; ++e) {
+        if (vi * 8 + e >= valid) v[i][e] = -INFINITY;   // padding columns (keys past the sequence end) get weight 0
+        mx = fmaxf(mx, v[i][e]);
+      }
     }
   }
   auto block_reduce = [&](float val, bool is_max) {
@@ -909,7 +913,18 @@ extern "C" int ih_softmax_rows_f16(void* x, long long ld, long long rows, int co
            "ih_softmax_rows_f16: cols must be a multiple of 8 and <= %d", SMX_THREADS * SMX_MAXV * 8);
   IH_CHECK(rows <= 0x7fffffffLL, IH_ERR_SHAPE, "ih_softmax_rows_f16: too many rows");
   IH_CUDA(launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(SMX_THREADS), (size_t)0, (cudaStream_t)stream,
-                        (__half*)x, ld, cols));
+                        (__half*)x, ld, cols, cols));
+  return 0;
+}
+
+extern "C" int ih_softmax_rows_masked_f16(void* x, long long ld, long long rows, int cols, int valid_cols, void* stream) {
+  IH_CHECK(x && rows > 0 && cols > 0 && valid_cols > 0 && valid_cols <= cols, IH_ERR_ARG,
+           "ih_softmax_rows_masked_f16: bad arguments");
+  IH_CHECK(cols % 8 == 0 && ld % 8 == 0 && cols <= SMX_THREADS * SMX_MAXV * 8, IH_ERR_SHAPE,
+           "ih_softmax_rows_masked_f16: cols must be a multiple of 8 and <= %d", SMX_THREADS * SMX_MAXV * 8);
+  IH_CHECK(rows <= 0x7fffffffLL, IH_ERR_SHAPE, "ih_softmax_rows_masked_f16: too many rows");
+  IH_CUDA(launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(SMX_THREADS), (size_t)0, (cudaStream_t)stream,
+                        (__half*)x, ld, cols, valid_cols));
   return 0;
 }
 

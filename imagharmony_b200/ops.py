@@ -51,7 +51,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
            rows_per_group: int = 0, geglu: bool = False, silu: bool = False, gelu: bool = False,
            out: Optional[torch.Tensor] = None, tile_n: int = 0, ln=None,
-           stats_out: Optional[torch.Tensor] = None, quick_gelu: bool = False) -> torch.Tensor:
+           stats_out: Optional[torch.Tensor] = None, quick_gelu: bool = False, alpha: float = 1.0) -> torch.Tensor:
     """out = epi(x @ w.T + bias + rowbias[row // rows_per_group]) + residual ; x [M,K], w [N,K] (nn.Linear layout).
 
     LayerNorm folding: `stats_out` (float32 [ceil(N/64), M, 2]) receives per-row / per-64-column (sum, sumsq) of the
@@ -70,6 +70,14 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
     epi = ((EPI_GEGLU if geglu else 0) | (EPI_SILU if silu else 0) | (EPI_GELU if gelu else 0)
            | (EPI_QUICK_GELU if quick_gelu else 0))
+    if alpha != 1.0:
+        # out = epi(alpha * x w^T + bias) + residual (ih_gemm_scaled_f16: the VAE decoder's scaled residual stream)
+        if ln is not None or stats_out is not None or rowbias is not None or tile_n:
+            raise IHError("linear: alpha != 1 cannot be combined with ln / stats_out / rowbias / tile_n")
+        rc = lib.ih_gemm_scaled_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(residual), ldr, out.data_ptr(),
+                                    _rows(out, "out"), M, N, K, epi, float(alpha), _stream())
+        check(rc, "ih_gemm_scaled_f16")
+        return out
     if ln is None and stats_out is None:
         rc = lib.ih_gemm_f16(x.data_ptr(), _rows(x, "x"), w.data_ptr(), _p(bias), _p(rowbias), rows_per_group, ldrb,
                              _p(residual), ldr, out.data_ptr(), _rows(out, "out"), M, N, K, epi, tile_n, _stream())
@@ -111,7 +119,7 @@ def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.T
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
             rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, stride: int = 1,
-            out: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, tile_n: int = 0, alpha: float = 1.0) -> torch.Tensor:
     """3x3 conv, pad 1. x NHWC [B,H,W,Cin]; w_packed [Cout, 9*Cin] (see pack_conv3x3_weight); rowbias [B, >=Cout]."""
     lib = _lib.load()
     _req(x, "x"); _req(w_packed, "w")
@@ -125,6 +133,13 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
     if residual is not None and (not residual.is_contiguous() or residual.shape != out.shape):
         raise IHError("conv3x3: residual must be contiguous and shaped like the output")
+    if alpha != 1.0:
+        if rowbias is not None or tile_n:
+            raise IHError("conv3x3: alpha != 1 cannot be combined with rowbias / tile_n")
+        rc = lib.ih_conv2d_scaled_f16(x.data_ptr(), w_packed.data_ptr(), _p(bias), _p(residual), out.data_ptr(), B, H, W,
+                                      Cin, Cout, stride, float(alpha), _stream())
+        check(rc, "ih_conv2d_scaled_f16")
+        return out
     rc = lib.ih_conv2d_f16(x.data_ptr(), w_packed.data_ptr(), _p(bias), _p(rowbias), ldrb, _p(residual),
                            out.data_ptr(), B, H, W, Cin, Cout, 3, stride, tile_n, _stream())
     check(rc, "ih_conv2d_f16")
@@ -163,7 +178,7 @@ def _attn_workspace(device, need: int) -> Optional[torch.Tensor]:
         if torch.cuda.is_current_stream_capturing():
             raise IHError("attention workspace must be created before CUDA-graph capture (run one warm-up step)")
         had = ws is not None
-        ws = torch.empty(max(need, 16 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(need, 16 << 20), dtype=torch.uint8, device=device)   # arrival counters start at zero
         _attn_ws[device] = ws
         if had:
             _bump_generation()
@@ -467,6 +482,17 @@ def im2col3x3_nchw(x_nchw: torch.Tensor, kpad: int = 64, out: Optional[torch.Ten
     check(lib.ih_im2col3x3_nchw_f16(x_nchw.data_ptr(), out.data_ptr(), B, Cin, H, W, kpad, _stream()),
           "ih_im2col3x3_nchw_f16")
     return out
+
+
+def softmax_rows_masked_(x: torch.Tensor, valid_cols: int) -> torch.Tensor:
+    """softmax_rows_ over the first `valid_cols` columns of each row; the remaining (padding) columns become 0."""
+    lib = _lib.load()
+    _req(x, "x")
+    if x.dim() != 2 or not 0 < valid_cols <= x.shape[1]:
+        raise IHError("softmax_rows_masked_: 2-D matrix and 0 < valid_cols <= cols required")
+    check(lib.ih_softmax_rows_masked_f16(x.data_ptr(), _rows(x, "x"), x.shape[0], x.shape[1], int(valid_cols), _stream()),
+          "ih_softmax_rows_masked_f16")
+    return x
 
 
 def nhwc_to_nchw(x: torch.Tensor, C: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -53,6 +53,14 @@ int ih_gemm_ln_f16(const void* a, long long lda, const void* w, const void* bias
                    long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats, int ln_slabs,
                    float ln_eps, void* stats_out, void* stream);
 
+/* out = epi(alpha * (A W^T) + bias) + residual: ih_gemm_f16 with an output scale.  Used by the VAE decoder's SCALED
+ * RESIDUAL STREAM (scope row f1): the reference upcasts the SDXL VAE to fp32 because its activations overflow fp16
+ * (custom_pipelines.py:366-371); here the residual stream is stored as 2^-k * x (GroupNorm is scale-invariant, every
+ * conv / linear that writes the stream scales its output and bias by 2^-k), which is exact in real arithmetic. */
+int ih_gemm_scaled_f16(const void* a, long long lda, const void* w, const void* bias, const void* residual,
+                       long long ldr, void* out, long long ldo, int M, int N, int K, int epilogue, float alpha,
+                       void* stream);
+
 /* Debug aid: CTA 0 of later GEMM / conv launches writes %globaltimer stamps into this device buffer (>= 16 uint64);
  * NULL disables.  Not used on the product path. */
 void ih_gemm_set_trace(void* device_buffer);
@@ -63,6 +71,9 @@ void ih_gemm_set_trace(void* device_buffer);
 int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
                   const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
                   int tile_n, void* stream);
+/* out = alpha * conv(x) + bias + residual (3x3, pad 1): the VAE decoder's scaled residual stream, see ih_gemm_scaled_f16. */
+int ih_conv2d_scaled_f16(const void* x, const void* w, const void* bias, const void* residual, void* out, int B, int Hin,
+                         int Win, int Cin, int Cout, int stride, float alpha, void* stream);
 
 /* Multi-head attention, head_dim 64, softmax scale 1/8, no mask.
  *   q: [B, Nq, *] rows with ldq elements per row, head h at columns [h*64, h*64+64) (same for k, v, out).
@@ -75,10 +86,11 @@ int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk,
                      void* out, long long ldo, int B, int H, int Nq, int Nk, int n_ip, float ip_scale,
                      void* stream);
 
-/* ih_attention_f16 with a caller-owned scratch buffer (>= ih_attention_workspace_bytes(...) bytes, contents
- * irrelevant).  With it the long self-attention shapes (Nk > 96, n_ip == 0) cut the query tiles that would otherwise
- * form a nearly empty last wave into KV parts that share one wave and are merged by a second small kernel
- * (flash-decoding style, fixed merge order: deterministic).  workspace == NULL behaves like ih_attention_f16. */
+/* ih_attention_f16 with a caller-owned scratch buffer (>= ih_attention_workspace_bytes(...) bytes, ZERO-FILLED once
+ * by the caller; the kernels leave its arrival counters at zero).  With it the long self-attention shapes (Nk > 96,
+ * n_ip == 0) cut the query tiles that would otherwise form a nearly empty last wave into KV parts that share one wave;
+ * the last part of a tile to finish merges all partials inside the same kernel (flash-decoding style, fixed merge
+ * order: deterministic, no second launch).  workspace == NULL behaves like ih_attention_f16. */
 long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip);
 /* Fused front half of a cross-attention layer: out = CrossAttn(LayerNorm(h) Wq^T, k, v) for short key axes (Nk <= 96,
  * Nq % 128 == 0): the q projection (K input channels -> H*64) runs as a tcgen05 GEMM whose epilogue performs the
@@ -142,6 +154,8 @@ int ih_mean_tokens_f16(const void* x, void* out, int B, int n, int D, void* stre
  * two ih_gemm_f16 calls it forms the single-head, head_dim-512 attention of the VAE decoder mid block
  * ([3P] diffusers AutoencoderKL, called at custom_pipelines.py:373). */
 int ih_softmax_rows_f16(void* x, long long ld, long long rows, int cols, void* stream);
+/* same, with only the first valid_cols columns of every row taking part; the padding columns are written as 0. */
+int ih_softmax_rows_masked_f16(void* x, long long ld, long long rows, int cols, int valid_cols, void* stream);
 
 /* Nearest-neighbour 2x upsample NHWC [B,H,W,C] -> [B,2H,2W,C]. */
 int ih_upsample2x_f16(const void* x, void* out, int B, int H, int W, int C, void* stream);
