@@ -79,6 +79,7 @@ class VAEConfig:
     scaling_factor: float = 0.13025
     sample_size: int = 1024               # tiling: tiles of sample_size pixels (= sample_size / 8 latents), 25 % overlap
     tile_overlap_factor: float = 0.25
+    force_upcast: bool = True             # vae/config.json of SDXL-base: the reference upcasts the VAE to fp32 (custom_pipelines.py:366-371)
 
     @property
     def tile_latent_min_size(self) -> int:

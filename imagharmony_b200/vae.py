@@ -9,17 +9,23 @@ a key map.  Every operator runs on the sm_100a kernels of this package:
   (zero padding applies to the ones channel too, which makes the folded bias exact at the image border) and the folded
   weight W'[o, (c, tap)] = sum_m conv_in[o, m, tap] * pqc[m, c] / scaling_factor multiplies it;
 * ResnetBlock2D (no time embedding): GroupNorm+SiLU kernel -> implicit-GEMM conv3x3 (residual fused in conv2);
-* mid-block attention (1 head, head_dim = C = 512, N = h*w tokens): fused q|k|v GEMM (1/sqrt(C) folded into q), scores
-  q k^T by the GEMM kernel, `ih_softmax_rows_f16`, P v by the GEMM kernel, out projection with fused residual;
+* mid-block attention (1 head, head_dim = C = 512, N = h*w tokens): q / k GEMMs (1/sqrt(C) folded into q), V^T = W_v h^T
+  by a GEMM, then per block of <= 64 MiB of scores: q k^T (GEMM) -> `ih_softmax_rows_masked_f16` -> P V + b_v (GEMM);
+  out projection with fused residual;
 * nearest 2x upsample + conv3x3; conv_out with Cout padded 3 -> 16 and a gather to NCHW.
 
-Numerics: fp16 storage / fp32 accumulation like the UNet.  The reference upcasts the VAE to fp32 because the ORIGINAL
-SDXL VAE weights overflow in fp16 (custom_pipelines.py:366-371); this decoder is meant for fp16-safe weights (the
-widely used fp16-fix checkpoint) and for the random-init benchmark weights.  A TF32 / split-bf16 variant for the original
-checkpoint is future work.
+Numerics: fp16 storage / fp32 accumulation like the UNet.  The reference upcasts the VAE to fp32 when
+`vae.config.force_upcast` is set, because the ORIGINAL SDXL VAE's activations overflow fp16 (custom_pipelines.py:366-371).
+The native equivalent is a SCALED RESIDUAL STREAM: the decoder's residual stream (conv_in output, every ResBlock /
+attention / upsampler output) is stored as s * x with s = 2^-7.  GroupNorm is scale invariant (GN(s x; eps s^2) = GN(x; eps)),
+so each consumer normalises the scaled stream directly; every conv / linear that WRITES the stream scales its
+accumulator and bias by s in the GEMM epilogue (`alpha`), shortcuts / upsampler convs are linear in the stream and only
+scale their bias.  In real arithmetic this is exact; in fp16 it moves the representable range from 6.5e4 to 8.4e6 while
+the weights stay untouched.  `force_upcast = False` configurations (the fp16-fix checkpoint) run with s = 1.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional
 
 import torch
@@ -28,6 +34,11 @@ import torch.nn as nn
 from . import ops
 from ._lib import IHError
 from .config import SDXL_VAE, VAEConfig
+
+
+def _scaled(t: torch.Tensor, s: float) -> torch.Tensor:
+    """bias * s in the parameter dtype (s is a power of two: exact unless the product is subnormal)."""
+    return t.detach() if s == 1.0 else (t.detach().float() * s).to(t.dtype).contiguous()
 
 
 class VAEResnetBlock(nn.Module):
@@ -40,26 +51,41 @@ class VAEResnetBlock(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
         self._w1 = self._w2 = self._wsc = None
+        self._s = 1.0
 
-    def finalize(self):
+    def finalize(self, s: float = 1.0):
+        self._s = s
         self._w1 = ops.pack_conv3x3_weight(self.conv1.weight.detach())
         self._w2 = ops.pack_conv3x3_weight(self.conv2.weight.detach())
+        self._b1, self._b2 = _scaled(self.conv1.bias, s), _scaled(self.conv2.bias, s)
         if self.conv_shortcut is not None:
             self._wsc = self.conv_shortcut.weight.detach().reshape(self.cout, self.cin).contiguous()
+            self._bsc = _scaled(self.conv_shortcut.bias, s)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x = s * (residual stream); returns s * (block output).  conv1's output only feeds norm2, so it is kept at the
+        same scale s (its magnitude follows the stream's in the original VAE)."""
         B, H, W, _ = x.shape
-        h = ops.groupnorm(x, self.norm1.weight, self.norm1.bias, groups=self.groups, eps=1e-6, silu=True)
-        h = ops.conv3x3(h, self._w1, self.conv1.bias)
-        h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=1e-6, silu=True)
+        s = self._s
+        eps = 1e-6 * s * s
+        h = ops.groupnorm(x, self.norm1.weight, self.norm1.bias, groups=self.groups, eps=eps, silu=True)
+        h = ops.conv3x3(h, self._w1, self._b1, alpha=s)
+        h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=eps, silu=True)
         sc = x
-        if self.conv_shortcut is not None:
-            sc = ops.linear(x.reshape(B * H * W, self.cin), self._wsc, self.conv_shortcut.bias).reshape(B, H, W, self.cout)
-        return ops.conv3x3(h, self._w2, self.conv2.bias, residual=sc)
+        if self.conv_shortcut is not None:       # linear in the (scaled) stream: only the bias is scaled
+            sc = ops.linear(x.reshape(B * H * W, self.cin), self._wsc, self._bsc).reshape(B, H, W, self.cout)
+        return ops.conv3x3(h, self._w2, self._b2, residual=sc, alpha=s)
 
 
 class VAEAttention(nn.Module):
-    """diffusers `Attention(heads=1, dim_head=C, norm_num_groups, residual_connection=True, bias=True)`."""
+    """diffusers `Attention(heads=1, dim_head=C, norm_num_groups, residual_connection=True, bias=True)`.
+
+    One head of width C = 512 over N = h * w tokens.  The N x N score matrix is never materialised whole: queries are
+    processed in blocks sized so that a block of fp16 scores stays within 64 MiB (L2-resident on B200: 2048 query rows at
+    N = 16384, the 1024^2 image), each block = scores GEMM -> masked row softmax -> P V GEMM on the tensor-core kernel.
+    V^T comes straight out of a GEMM (W_v h^T), and the v bias is added after P V (softmax rows sum to one)."""
+
+    SCORE_BLOCK_BYTES = 64 << 20
 
     def __init__(self, ch: int, groups: int):
         super().__init__()
@@ -69,15 +95,16 @@ class VAEAttention(nn.Module):
         self.to_k = nn.Linear(ch, ch)
         self.to_v = nn.Linear(ch, ch)
         self.to_out = nn.ModuleList([nn.Linear(ch, ch), nn.Dropout(0.0)])
-        self._w_qkv = self._b_qkv = None
+        self._w_q = self._b_q = None
+        self._s = 1.0
 
-    def finalize(self):
-        s = self.ch ** -0.5                                      # softmax scale folded into the q projection
+    def finalize(self, s: float = 1.0):
+        self._s = s
+        sc = self.ch ** -0.5                                     # softmax scale folded into the q projection
         dt = self.to_q.weight.dtype
-        self._w_qkv = torch.cat([self.to_q.weight.detach().float() * s, self.to_k.weight.detach().float(),
-                                 self.to_v.weight.detach().float()], 0).to(dt).contiguous()
-        self._b_qkv = torch.cat([self.to_q.bias.detach().float() * s, self.to_k.bias.detach().float(),
-                                 self.to_v.bias.detach().float()], 0).to(dt).contiguous()
+        self._w_q = (self.to_q.weight.detach().float() * sc).to(dt).contiguous()
+        self._b_q = (self.to_q.bias.detach().float() * sc).to(dt).contiguous()
+        self._b_o = _scaled(self.to_out[0].bias, s)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
@@ -85,28 +112,30 @@ class VAEAttention(nn.Module):
         Np = (N + 7) // 8 * 8                 # the GEMM / softmax kernels want multiples of 8: pad keys, mask their scores
         if Np > 32768:
             raise IHError(f"VAE mid-block attention: {N} tokens exceed 32768 (enable_vae_tiling() decodes 128x128 tiles)")
-        h = ops.groupnorm(x, self.group_norm.weight, self.group_norm.bias, groups=self.groups, eps=1e-6, silu=False)
-        qkv = ops.linear(h.reshape(B * N, C), self._w_qkv, self._b_qkv)            # [B*N, 3C]
+        s = self._s
+        h = ops.groupnorm(x, self.group_norm.weight, self.group_norm.bias, groups=self.groups, eps=1e-6 * s * s, silu=False)
+        h2 = h.reshape(B * N, C)
+        q = ops.linear(h2, self._w_q, self._b_q)                                    # [B*N, C], 1/sqrt(C) folded in
+        k = ops.linear(h2, self.to_k.weight, self.to_k.bias)
         o = torch.empty((B * N, C), dtype=x.dtype, device=x.device)
-        for b in range(B):                                                          # one image at a time: S is N x N
-            rows = slice(b * N, (b + 1) * N)
-            if Np == N:
-                q = qkv[rows, :C]
-                k = qkv[rows, C:2 * C].contiguous()
-                vt = qkv[rows, 2 * C:].t().contiguous()                             # [C, N]: right-hand operand of P v
-            else:                                                                   # odd edge tiles of a tiled decode
-                pad = torch.zeros((Np, 3 * C), dtype=x.dtype, device=x.device)
-                pad[:N] = qkv[rows]
-                q, k, vt = pad[:, :C], pad[:, C:2 * C].contiguous(), pad[:, 2 * C:].t().contiguous()
-            s = ops.linear(q, k)                                                    # scores (scale already in q)
-            if Np != N:
-                s[:, N:] = float("-inf")                                            # padded keys get no weight
-            ops.softmax_rows_(s)
-            if Np == N:
-                ops.linear(s, vt, out=o[rows])
-            else:
-                o[rows] = ops.linear(s, vt)[:N]
-        out = ops.linear(o, self.to_out[0].weight, self.to_out[0].bias, residual=x.reshape(B * N, C))
+        block = max(128, min((N + 127) // 128 * 128, self.SCORE_BLOCK_BYTES // (2 * Np) // 128 * 128))
+        scores = torch.empty((block, Np), dtype=x.dtype, device=x.device)           # reused by every block
+        vt = (torch.empty if Np == N else torch.zeros)((C, Np), dtype=x.dtype, device=x.device)
+        for b in range(B):                                                          # one image at a time
+            hb, kb = h2[b * N:(b + 1) * N], k[b * N:(b + 1) * N]
+            if Np != N:                                                             # odd edge tiles of a tiled decode
+                hp = torch.zeros((Np, C), dtype=x.dtype, device=x.device)
+                kp = torch.zeros((Np, C), dtype=x.dtype, device=x.device)
+                hp[:N], kp[:N] = hb, kb
+                hb, kb = hp, kp
+            ops.linear(self.to_v.weight, hb, out=vt)                                # V^T = W_v h^T  [C, Np]
+            for r0 in range(0, N, block):
+                rows = min(block, N - r0)
+                sc = scores[:rows]
+                ops.linear(q[b * N + r0: b * N + r0 + rows], kb, out=sc)            # scores (scale already in q)
+                ops.softmax_rows_masked_(sc, N)                                     # padded keys get no weight
+                ops.linear(sc, vt, self.to_v.bias, out=o[b * N + r0: b * N + r0 + rows])   # P V + b_v
+        out = ops.linear(o, self.to_out[0].weight, self._b_o, residual=x.reshape(B * N, C), alpha=s)
         return out.reshape(B, H, W, C)
 
 
@@ -116,11 +145,12 @@ class VAEUpsample(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
         self._w = None
 
-    def finalize(self):
+    def finalize(self, s: float = 1.0):
         self._w = ops.pack_conv3x3_weight(self.conv.weight.detach())
+        self._b = _scaled(self.conv.bias, s)
 
     def forward(self, x):
-        return ops.conv3x3(ops.upsample2x(x), self._w, self.conv.bias)
+        return ops.conv3x3(ops.upsample2x(x), self._w, self._b)     # linear in the scaled stream: only the bias scales
 
 
 class VAEMidBlock(nn.Module):
@@ -176,12 +206,19 @@ class AutoencoderKLDecoder(nn.Module):
         self.decoder = Decoder(cfg)
         self._w_in = self._w_out = self._b_out = None
         self.use_tiling = False             # pipeline.enable_vae_tiling() (test.py:73)
+        # scale of the stored residual stream (module docstring): 2^-7 when the configuration asks for the fp32 upcast
+        self.stream_scale = 2.0 ** -7 if getattr(cfg, "force_upcast", True) else 1.0
 
     # ---- construction ------------------------------------------------------------------------------------------
     @classmethod
-    def from_state_dict(cls, cfg: VAEConfig, sd: Dict[str, torch.Tensor], device="cuda") -> "AutoencoderKLDecoder":
+    def from_state_dict(cls, cfg: VAEConfig, sd: Dict[str, torch.Tensor], device="cuda",
+                        stream_scale: Optional[float] = None) -> "AutoencoderKLDecoder":
         with torch.device("meta"):
             m = cls(cfg)
+        if stream_scale is not None:
+            if stream_scale <= 0 or math.log2(stream_scale) != int(math.log2(stream_scale)):
+                raise IHError("stream_scale must be a power of two")
+            m.stream_scale = float(stream_scale)
         m = m.to_empty(device=device)
         own = m.state_dict()
         missing = [k for k in own if k not in sd]
@@ -193,9 +230,11 @@ class AutoencoderKLDecoder(nn.Module):
         return m
 
     def finalize(self) -> None:
+        s = self.stream_scale
         for mod in self.modules():
             if isinstance(mod, (VAEResnetBlock, VAEAttention, VAEUpsample)):
-                mod.finalize()
+                mod.finalize(s)
+        self._b_in = _scaled(self.decoder.conv_in.bias, s)
         cfg = self.config
         L = cfg.latent_channels
         w_in = self.decoder.conv_in.weight.detach().float()                          # [C, L, 3, 3]
@@ -277,12 +316,13 @@ class AutoencoderKLDecoder(nn.Module):
         ones = torch.ones((B, 1, h, w), dtype=dt, device=latents.device)
         z5 = torch.cat([latents.to(dt), ones], dim=1).contiguous()
         a = ops.im2col3x3_nchw(z5, self._w_in.shape[1])
-        x = ops.linear(a, self._w_in, dec.conv_in.bias).reshape(B, h, w, -1)           # post_quant_conv + /sf + conv_in
+        s = self.stream_scale
+        x = ops.linear(a, self._w_in, self._b_in, alpha=s).reshape(B, h, w, -1)        # s * (post_quant_conv + /sf + conv_in)
         x = dec.mid_block(x)
         for blk in dec.up_blocks:
             x = blk(x)
         g = self.config.norm_num_groups
-        x = ops.groupnorm(x, dec.conv_norm_out.weight, dec.conv_norm_out.bias, groups=g, eps=1e-6, silu=True)
+        x = ops.groupnorm(x, dec.conv_norm_out.weight, dec.conv_norm_out.bias, groups=g, eps=1e-6 * s * s, silu=True)
         x = ops.conv3x3(x, self._w_out, self._b_out)
         return ops.nhwc_to_nchw(x, self.config.out_channels)
 

@@ -31,9 +31,9 @@ def fold_layernorm(w, bias, gamma, beta):
 
 
 def linear(x, w, bias=None, *, residual=None, rowbias=None, rows_per_group=0, geglu=False, silu=False, gelu=False,
-           out=None, tile_n=0, ln=None, stats_out=None, quick_gelu=False):
+           out=None, tile_n=0, ln=None, stats_out=None, quick_gelu=False, alpha=1.0):
     _count[0] += 1
-    y = x.float() @ w.float().t()
+    y = (x.float() @ w.float().t()) * alpha
     if ln is not None:
         st, eps = ln
         K = x.shape[1]
@@ -84,6 +84,14 @@ def softmax_rows_(x):
     return x
 
 
+def softmax_rows_masked_(x, valid_cols):
+    _count[0] += 1
+    y = torch.zeros_like(x, dtype=torch.float32)
+    y[:, :valid_cols] = torch.softmax(x[:, :valid_cols].float(), dim=-1)
+    x.copy_(y.to(x.dtype))
+    return x
+
+
 def add_bcast(a, b, out=None):
     _count[0] += 1
     return (a.reshape(-1, b.numel()) + b.reshape(1, -1)).reshape(a.shape)
@@ -99,12 +107,14 @@ def pack_conv3x3_weight(w):
     return w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
 
 
-def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, out=None, tile_n=0):
+def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, out=None, tile_n=0, alpha=1.0):
     _count[0] += 1
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     w = w_packed.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).float()
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, _f(bias), stride=stride, padding=1).permute(0, 2, 3, 1)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride=stride, padding=1).permute(0, 2, 3, 1) * alpha
+    if bias is not None:
+        y = y + bias.float()
     if rowbias is not None:
         y = y + rowbias.float()[:, None, None, :]
     if residual is not None:

@@ -62,3 +62,39 @@ def test_vae_tiled_decode_matches_oracle(patched):  # noqa: F811
     small = z[:, :, :8, :8].contiguous()
     with torch.no_grad():
         assert torch.allclose(native.decode(small), ref.decode(small), rtol=1e-4, atol=1e-4)
+
+
+def test_vae_scaled_residual_stream_is_exact_in_fp32(patched):  # noqa: F811
+    """The force_upcast replacement (module docstring of vae.py): storing the residual stream as 2^-k * x with scale-
+    invariant GroupNorms and alpha-scaled writers is the same function.  fp32 stand-in ops: identical to the oracle
+    for k = 0, 7, 10 -- including a model whose stream reaches 1e5 (it would overflow fp16 without the scaling)."""
+    from imagharmony_b200.config import TINY_VAE
+    native, ref = _pair(TINY_VAE, seed=5)
+    assert native.stream_scale == 2.0 ** -7          # TINY_VAE / SDXL_VAE ask for the upcast (force_upcast)
+    with torch.no_grad():
+        for m in (native, ref):                      # blow the residual stream up at its source
+            m.decoder.conv_in.weight.mul_(4000.0)
+            m.decoder.conv_in.bias.mul_(4000.0)
+    z = torch.randn(1, 4, 6, 5, generator=torch.Generator().manual_seed(3)) * TINY_VAE.scaling_factor * 3
+    with torch.no_grad():
+        r = ref.decode(z)
+    outs = []
+    for k in (0, 7, 10):
+        native.stream_scale = 2.0 ** -k
+        native.finalize()
+        with torch.no_grad():
+            outs.append(native.decode(z))
+        assert torch.allclose(outs[-1], r, rtol=2e-4, atol=2e-4), (k, (outs[-1] - r).abs().max())
+
+
+def test_vae_blocked_attention_matches_oracle(patched, monkeypatch):  # noqa: F811
+    """The mid-block attention in several query blocks (forced by a tiny score budget) and with padded keys (N % 8 != 0)."""
+    from imagharmony_b200 import vae as V
+    from imagharmony_b200.config import TINY_VAE
+    native, ref = _pair(TINY_VAE, seed=6)
+    monkeypatch.setattr(V.VAEAttention, "SCORE_BLOCK_BYTES", 128 * 2 * 304)    # 128 query rows per block
+    for hw in ((19, 16), (15, 11)):                                            # N = 304 (3 blocks), N = 165 (padded to 168)
+        z = torch.randn(1, 4, *hw, generator=torch.Generator().manual_seed(4)) * TINY_VAE.scaling_factor * 3
+        with torch.no_grad():
+            r, o = ref.decode(z), native.decode(z)
+        assert torch.allclose(o, r, rtol=1e-4, atol=1e-4), (hw, (o - r).abs().max())

@@ -90,3 +90,45 @@ def test_vae_tiled_decode_matches_oracle():
     print(f"[vae tiled] max|err| {err:.3e} max|ref| {mx:.3e}")
     assert o.shape == r.shape and torch.isfinite(o).all()
     assert err <= 1e-2 * mx, (err, mx)
+
+
+def test_softmax_rows_masked_kernel():
+    from imagharmony_b200 import ops
+    for rows, cols, valid in [(64, 1024, 1000), (7, 168, 165), (16, 16384, 16384)]:
+        x = (torch.randn(rows, cols, generator=torch.Generator("cpu").manual_seed(rows)) * 3).half().cuda()
+        ref = torch.zeros(rows, cols)
+        ref[:, :valid] = torch.softmax(x[:, :valid].float().cpu(), dim=-1)
+        ops.softmax_rows_masked_(x, valid)
+        assert torch.allclose(x.float().cpu(), ref, rtol=2e-3, atol=1e-6) and (x[:, valid:] == 0).all()
+
+
+def test_vae_scaled_stream_survives_fp16_overflow():
+    """The reference upcasts the SDXL VAE to fp32 because its activations overflow fp16 (custom_pipelines.py:366-371).
+    A decoder whose residual stream reaches ~1e5 (conv_in scaled up 4000x): the plain fp16 pipeline (stream_scale 1, and
+    the torch fp16 oracle) produces non-finite pixels, the scaled-stream pipeline (default 2^-7) matches the fp32 oracle."""
+    from imagharmony_b200.config import TINY_VAE as cfg
+    from imagharmony_b200.vae import AutoencoderKLDecoder
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    from oracle.vae_ref import VAEDecoderRef
+    with torch.device("meta"):
+        shapes = shapes_of(VAEDecoderRef(cfg))
+    sd = {k: v.float() for k, v in random_state_dict(shapes, 11).items()}
+    for k in ("decoder.conv_in.weight", "decoder.conv_in.bias"):
+        sd[k] = (sd[k] * 4000.0).half().float()              # stays fp16-representable (|w| < 65504)
+    ref32 = VAEDecoderRef(cfg)
+    ref32.load_state_dict(sd)
+    z = (torch.randn(2, 4, 16, 16, generator=torch.Generator("cpu").manual_seed(12)) * cfg.scaling_factor * 2).half()
+    with torch.no_grad():
+        r = ref32.eval().decode(z.float())
+        stream = ref32.decoder.conv_in(ref32.post_quant_conv(z.float() / cfg.scaling_factor))
+    assert stream.abs().max() > 65504, "the test model must overflow fp16"
+    native = AutoencoderKLDecoder.from_state_dict(cfg, sd, device="cuda")
+    assert native.stream_scale == 2.0 ** -7
+    o = native.decode(z.cuda()).float().cpu()
+    plain = AutoencoderKLDecoder.from_state_dict(cfg, sd, device="cuda", stream_scale=1.0).decode(z.cuda()).float().cpu()
+    torch.cuda.synchronize()
+    err, mx = (o - r).abs().max().item(), r.abs().max().item()
+    print(f"[vae scaled stream] stream max {stream.abs().max().item():.3e}: scaled max|err| {err:.3e} (max|ref| {mx:.3e}); "
+          f"plain fp16 finite: {bool(torch.isfinite(plain).all())}")
+    assert torch.isfinite(o).all() and err <= 1e-2 * mx, (err, mx)
+    assert not torch.isfinite(plain).all(), "without the scaled stream this model overflows fp16"
