@@ -980,6 +980,7 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p) {
 // KV-split plan of the ping-pong kernel: with P query pairs on G SMs (one CTA per SM), the last P mod G pairs would
 // run as a nearly empty extra wave; they are cut into `split` KV parts each so that (P mod G) * split <= G CTAs share
 // that wave.  Returns split (1 = none) and the number of pairs processed whole.
+constexpr long long A2_CNT_BYTES = 4096;   // 1024 arrival counters at the start of the attention workspace
 static long long* g_attn_trace = nullptr;
 static int g_split_policy = 0;   // 0: cost model, 1: split whenever a split plan exists (tests)
 
@@ -1012,10 +1013,10 @@ extern "C" long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, 
   int n_whole, split;
   const int pairs = B * H * ((Nq + 255) / 256);
   attn2_plan(pairs, (Nk + 127) / 128, &n_whole, &split);
-  // partial O rows + (m, l) per part, then one arrival counter per split pair (the caller provides ZEROED memory; the
-  // kernel leaves the counters at zero)
-  return (long long)(pairs - n_whole) * split * 256 * (64 + 2) * (long long)sizeof(float) +
-         (long long)(pairs - n_whole) * (long long)sizeof(int);
+  // arrival counters (one per split pair, FIXED place at the start of the buffer so that calls with different shapes
+  // share them: the caller provides zeroed memory once, every launch leaves them at zero), then partial O rows + (m, l)
+  if (pairs == n_whole) return 0;
+  return A2_CNT_BYTES + (long long)(pairs - n_whole) * split * 256 * (64 + 2) * (long long)sizeof(float);
 }
 
 extern "C" int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
@@ -1101,20 +1102,21 @@ extern "C" int ih_attention_ws_f16(const void* q, long long ldq, const void* k, 
     const int pairs = B * H * p.qpairs;
     attn2_plan(pairs, p.num_kv_blocks, &p.n_whole, &p.split);
     const long long slots = (long long)(pairs - p.n_whole) * p.split;
-    const long long need = slots * 256 * 66 * (long long)sizeof(float) + (long long)(pairs - p.n_whole) * (long long)sizeof(int);
+    const long long need = A2_CNT_BYTES + slots * 256 * 66 * (long long)sizeof(float);
     if (slots > 0 && (!workspace || workspace_bytes < need)) {
       p.n_whole = pairs;   // no (or too small a) workspace: every pair runs whole
       p.split = 1;
     }
     const int n_split_ctas = (pairs - p.n_whole) * p.split;
-    p.ws_o = (float*)workspace;
+    p.ws_o = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + A2_CNT_BYTES);
     p.ws_ml = p.ws_o + (long long)n_split_ctas * 256 * 64;
     // IH_ATTN_FUSED_MERGE=0: merge the parts with a second launch (attn_combine_kernel) instead of in-kernel
     static const bool fused_merge = [] {
       const char* e = getenv("IH_ATTN_FUSED_MERGE");
       return !(e && e[0] == '0');
     }();
-    p.ws_cnt = (fused_merge && n_split_ctas > 0) ? reinterpret_cast<int*>(p.ws_ml + (long long)n_split_ctas * 256 * 2) : nullptr;
+    p.ws_cnt = (fused_merge && n_split_ctas > 0 && pairs - p.n_whole <= A2_CNT_BYTES / (int)sizeof(int))
+                   ? reinterpret_cast<int*>(workspace) : nullptr;
     IH_CUDA(launch_kernel(attn2_f16_kernel, dim3(p.n_whole + n_split_ctas), dim3(A2_THREADS), (size_t)(A2_SMEM_BYTES),
                           (cudaStream_t)stream, tq, tk, tv, p));
     if (n_split_ctas > 0 && !p.ws_cnt)

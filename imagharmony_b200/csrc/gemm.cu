@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           named_bar_sync(2, GEMM_EPI_WARPS * 32);
         }
         tmem_ld_wait();
+        if (issuer && it == 0 && sl == 0) stamp(9);
         if (sl == last_slab) {
           // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
           arrived = true;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         }
         fence_proxy_async_smem();
         named_bar_sync(3, GEMM_EPI_WARPS * 32);        // the slab is complete in shared memory
+        if (issuer && it == 0) stamp(sl == last_slab ? 12 : (sl == 0 ? 10 : 11));
         if (issuer) {
           if (p.mode == 0) tma_store_2d(&omap, sbuf, col0, m_tile * BM);
           else tma_store_4d(&omap, sbuf, col0, x0, y0, img);
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
       // the staging buffers may be rewritten (next tile) / must stay valid (kernel end) until the bulk stores have read
       // them; global visibility is given by kernel completion (the next kernel's griddepcontrol.wait / stream order)
       if (issuer) tma_store_wait_read0();
+      if (issuer && it == 0) stamp(13);
     }
   }
 

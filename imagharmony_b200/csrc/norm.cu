@@ -4,6 +4,7 @@
 // (custom_pipelines.py:338-345); LayerNorm also serves ImageProjModel.norm (ip_adapter.py:47) and Resampler norms.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/ih_api.h"
 #include "host_util.h"
@@ -39,6 +40,7 @@ __device__ __forceinline__ void store8(__half* p, const float (&x)[8]) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GN_MAXG = 512;
 constexpr int GN_MAXB = 1024;
+constexpr int GN_SYNC_WORDS = 3 * GN_MAXB;   // per image: ticket (statistics), ready flag and departure counter (fused kernel)
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                                 int groups, int R, int rows_per_block, float eps, float* __restrict__ ws, int B) {
@@ -113,7 +115,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
   }
   __threadfence();
   __syncthreads();
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws) - GN_MAXB;  // ws points just past the ticket array
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws) - GN_SYNC_WORDS;  // ws points just past the sync arrays
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(&tickets[b], 1u);
     s_last = (t == gridDim.x - 1);
@@ -227,6 +229,203 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// GroupNorm in ONE launch: statistics pass, image-wide hand-over, apply pass.  Same decomposition as the two kernels
+// above (grid = (G row-chunks, B), every block owns a row range of one image).  After its partial sums are published,
+// the last block of an image finalises mean / rstd and raises `ready[b]`; all blocks of the image wait for that flag,
+// then normalise THEIR OWN rows (second read: L1 / L2 hits).  The host caps the grid at the number of co-resident
+// blocks (occupancy query), so the wait cannot deadlock; a bounded spin traps instead of hanging.  The last block to
+// leave an image resets the flags, so the workspace is reusable by the next launch (and by CUDA-graph replays).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int groups, int R, int rows_per_block, float eps, float* __restrict__ ws, int B,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta, int silu,
+                                __half* __restrict__ out) {
+  extern __shared__ float s_acc[];  // statistics: [R][2][C] per-row-lane partials; apply: scale[C], shift[C]
+  __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = C0 + C1;
+  const int CV = C >> 3;
+  const int b = blockIdx.y;
+  const int cv = threadIdx.x % CV;
+  const int rl = threadIdx.x / CV;
+  const int c = cv << 3;
+  const __half* src;
+  long long stride;
+  if (c < C0) {
+    src = x0 + (long long)b * HW * C0 + c;
+    stride = C0;
+  } else {
+    src = x1 + (long long)b * HW * C1 + (c - C0);
+    stride = C1;
+  }
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(HW, row_begin + rows_per_block);
+  const int cpg = C / groups;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws) - GN_SYNC_WORDS;
+  unsigned int* ready = tickets + GN_MAXB;
+  unsigned int* done = ready + GN_MAXB;
+  float* fin = ws + (long long)B * GN_MAXG * 2 * groups + (long long)b * 2 * groups;
+  // ---- statistics of my rows ----
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    int row = row_begin + rl;
+    for (; row + 3 * R < row_end; row += 4 * R) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(src + (long long)row * stride, v0);
+      load8(src + (long long)(row + R) * stride, v1);
+      load8(src + (long long)(row + 2 * R) * stride, v2);
+      load8(src + (long long)(row + 3 * R) * stride, v3);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+        q[e] += (v0[e] * v0[e] + v1[e] * v1[e]) + (v2[e] * v2[e] + v3[e] * v3[e]);
+      }
+    }
+    for (; row < row_end; row += R) {
+      float v[8];
+      load8(src + (long long)row * stride, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += v[e];
+        q[e] += v[e] * v[e];
+      }
+    }
+    float* mine = s_acc + (long long)rl * 2 * C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mine[c + e] = s[e];
+      mine[C + c + e] = q[e];
+    }
+  }
+  __syncthreads();
+  float* part = ws + ((long long)b * GN_MAXG + blockIdx.x) * 2 * groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float ds = 0.f, dq = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      const float* pr = s_acc + (long long)rr * 2 * C;
+      for (int i = 0; i < cpg; ++i) {
+        ds += pr[g * cpg + i];
+        dq += pr[C + g * cpg + i];
+      }
+    }
+    part[g] = ds;
+    part[groups + g] = dq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[b], 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double* s_red = reinterpret_cast<double*>(s_acc);  // reuse (>= 2*C floats >= 2*groups*slices doubles)
+    const int nv = 2 * groups;
+    int slices = blockDim.x / nv;
+    if (slices < 1) slices = 1;
+    if (slices > 4) slices = 4;
+    const float* pp = ws + (long long)b * GN_MAXG * nv;
+    __syncthreads();
+    if ((int)threadIdx.x < nv * slices) {
+      const int v = threadIdx.x % nv, sl = threadIdx.x / nv;
+      double a = 0.0;
+#pragma unroll 8
+      for (int k = sl; k < (int)gridDim.x; k += slices) a += (double)__ldcg(pp + (long long)k * nv + v);
+      s_red[sl * nv + v] = a;
+    }
+    __syncthreads();
+    const double n = (double)HW * cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      for (int sl = 0; sl < slices; ++sl) {
+        ds += s_red[sl * nv + g];
+        dq += s_red[sl * nv + groups + g];
+      }
+      const double mean = ds / n;
+      double var = dq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      fin[g] = (float)mean;
+      fin[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tickets[b] = 0u;            // self-reset for the next call
+      __threadfence();
+      atomicExch(&ready[b], 1u);  // mean / rstd of image b are published
+    }
+  }
+  // ---- image-wide hand-over ----
+  if (threadIdx.x == 0) {
+    unsigned int spins = 0;
+    while (atomicAdd(&ready[b], 0u) == 0u) {
+      __nanosleep(32);
+      if (++spins > IH_SPIN_LIMIT) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- apply to my rows ----
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const float mean = __ldcg(fin + g), rstd = __ldcg(fin + groups + g);
+    const float ga = __half2float(gamma[ch]), be = __half2float(beta[ch]);
+    s_acc[ch] = ga * rstd;
+    s_acc[C + ch] = be - mean * ga * rstd;
+  }
+  __syncthreads();
+  {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = s_acc[c + e];
+      sh[e] = s_acc[C + c + e];
+    }
+    __half* dst = out + (long long)b * HW * C + c;
+    int row = row_begin + rl;
+    for (; row + 3 * R < row_end; row += 4 * R) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(src + (long long)(row + u * R) * stride, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = v[u][e] * sc[e] + sh[e];
+          if (silu) y = silu_f(y);
+          v[u][e] = y;
+        }
+        store8(dst + (long long)(row + u * R) * C, v[u]);
+      }
+    }
+    for (; row < row_end; row += R) {
+      float v[8];
+      load8(src + (long long)row * stride, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = v[e] * sc[e] + sh[e];
+        if (silu) y = silu_f(y);
+        v[e] = y;
+      }
+      store8(dst + (long long)row * C, v);
+    }
+  }
+  // ---- departure: the last block of the image to get here re-arms the flags ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int d = atomicAdd(&done[b], 1u);
+    if (d == gridDim.x - 1) {
+      done[b] = 0u;
+      ready[b] = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LayerNorm: one 16-byte vector per thread, TPR (multiple of 32) threads per row, several rows per block.
 // two-pass (mean, then centred variance) in registers.
 // ---------------------------------------------------------------------------------------------------------------
@@ -288,7 +487,7 @@ using namespace ih;
 
 extern "C" long long ih_groupnorm_workspace_bytes(int B, int groups) {
   return ((long long)B * GN_MAXG * 2 * groups + (long long)B * 2 * groups) * (long long)sizeof(float) +
-         (long long)GN_MAXB * (long long)sizeof(unsigned int);
+         (long long)GN_SYNC_WORDS * (long long)sizeof(unsigned int);
 }
 
 extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, const void* gamma, const void* beta,
@@ -319,8 +518,31 @@ extern "C" int ih_groupnorm_f16(const void* x0, int C0, const void* x1, int C1, 
   int rows_per_block = (HW + G - 1) / G;
   if (rows_per_block < 4 * R) rows_per_block = 4 * R;
   G = (HW + rows_per_block - 1) / rows_per_block;
+  float* ws = (float*)((unsigned int*)stats_ws + GN_SYNC_WORDS);
+  // One launch (statistics -> hand-over -> apply) when every block of the grid can be resident at once; IH_GN_FUSED=0
+  // keeps the two-kernel form.
+  static const bool fused_env = [] {
+    const char* e = getenv("IH_GN_FUSED");
+    return !(e && e[0] == '0');
+  }();
+  if (fused_env) {
+    const size_t smem = (size_t)R * 2 * C * sizeof(float);
+    int occ = 0;
+    IH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, threads, smem));
+    const long long capacity = (long long)occ * num_sms();
+    int Gf = G;
+    if ((long long)Gf * B > capacity) Gf = (int)(capacity / B);
+    if (Gf >= 1) {
+      int rpb = (HW + Gf - 1) / Gf;
+      if (rpb < 4 * R) rpb = 4 * R;
+      Gf = (HW + rpb - 1) / rpb;
+      IH_CUDA(launch_kernel(gn_fused_kernel, dim3(Gf, B), dim3(threads), smem, stream, (const __half*)x0, C0,
+                            (const __half*)x1, C1, HW, groups, R, rpb, eps, ws, B, (const __half*)gamma,
+                            (const __half*)beta, silu, (__half*)out));
+      return 0;
+    }
+  }
   dim3 grid(G, B);
-  float* ws = (float*)((unsigned int*)stats_ws + GN_MAXB);
   IH_CUDA(launch_kernel(gn_stats_kernel, dim3(grid), dim3(threads), (size_t)((size_t)R * 2 * C * sizeof(float)), stream, (const __half*)x0, C0, (const __half*)x1, C1, HW,
                                                                      groups, R, rows_per_block, eps, ws, B));
   const float* fin = ws + (long long)B * GN_MAXG * 2 * groups;
