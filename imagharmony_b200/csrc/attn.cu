@@ -389,11 +389,20 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
     tc_fence_after();
     const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
     const uint64_t v_desc = umma_desc_sw128(smem_u32(sV));
+    // Two accumulating MMAs over UN-normalised probabilities (the row thread evaluates every exponential once):
+    //   O_text (TMEM columns [0, 64))   = P_text V   -- P_text is zero at the image-prompt keys
+    //   O_ip   (TMEM columns [64, 128)) = P_ip   V   -- P_ip covers the (<= 64) keys from ip_base on, in the Q buffer
+    // both overlay the (already consumed) S columns; the epilogue forms O_text / l_text + scale * O_ip / l_ip.
+    const int n_text = p.Nk - p.n_ip;
+    const int ksteps_t = (n_text + 15) >> 4;
+    const int ip_k0 = n_text >> 4;                       // first 16-key step that holds an image-prompt key
+    const int ksteps_i = p.n_ip > 0 ? ((p.Nk + 15) >> 4) - ip_k0 : 0;
     if (elect_one()) {
-#pragma unroll
-      for (int kk = 0; kk < 6; ++kk)   // O overlays the (already consumed) S columns
+      for (int kk = 0; kk < ksteps_t; ++kk)
         umma_f16_ss(tmem_base, p_desc + ((kk >> 2) * (ATT_TILE >> 4) + 2 * (kk & 3)), v_desc + kk * (2048 >> 4), idesc_o,
                     kk != 0);
+      for (int kk = 0; kk < ksteps_i; ++kk)
+        umma_f16_ss(tmem_base + 64, q_desc + 2 * kk, v_desc + (ip_k0 + kk) * (2048 >> 4), idesc_o, kk != 0);
       umma_commit(o_full);
     }
     __syncwarp();
@@ -402,10 +411,12 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
     const int r = q * 32 + lane;
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* p_row = sP + r * 128;
+    uint8_t* pi_row = sQ + r * 128;      // P_ip reuses the Q tile (free once S has been computed)
     const int rx = r & 7;
     const float sl2 = p.scale_log2;
     const int valid = p.Nk;              // <= 96
     const int n_text = valid - p.n_ip;
+    const int ip_chunk0 = (n_text >> 4) << 1;   // first 8-key chunk of the P_ip tile (16-key aligned)
 
     mbar_wait(s_full, 0);
     tc_fence_after();
@@ -425,50 +436,48 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
       }
     }
     const float m_t = mx_t * sl2, m_i = mx_i * sl2;
-    // pass 2: denominators
+    // pass 2: every exponential ONCE: p = 2^(s * scale - m_segment), un-normalised, into the fp16 P tiles; the row sums
+    // normalise the output rows in the epilogue (keys 96..127 of the second half are never read by the MMA)
     float l_t = 0.f, l_i = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tS + c * 32, v);
       tmem_ld_wait();
+      float pt[32], pi[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const int col = c * 32 + e;
         const float s = __uint_as_float(v[e]);
-        if (col < n_text) l_t += ex2_approx(fmaf(s, sl2, -m_t));
-        else if (col < valid) l_i += ex2_approx(fmaf(s, sl2, -m_i));
-      }
-    }
-    const float inv_t = 1.f / l_t;
-    const float inv_i = (p.n_ip > 0) ? p.ip_scale / l_i : 0.f;
-    // pass 3: normalised probabilities -> fp16 P tile (keys 96..127 of the second half are never read by the MMA)
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tS + c * 32, v);
-      tmem_ld_wait();
-      float pr[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int col = c * 32 + e;
-        const float s = __uint_as_float(v[e]);
-        float pv = 0.f;
-        if (col < n_text) pv = ex2_approx(fmaf(s, sl2, -m_t)) * inv_t;
-        else if (col < valid) pv = ex2_approx(fmaf(s, sl2, -m_i)) * inv_i;
-        pr[e] = pv;
+        const bool is_t = col < n_text, is_i = !is_t && col < valid;
+        const float ex = ex2_approx(fmaf(s, sl2, is_t ? -m_t : -m_i));
+        pt[e] = is_t ? ex : 0.f;
+        pi[e] = is_i ? ex : 0.f;
+        l_t += pt[e];
+        l_i += pi[e];
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int chunk = c * 4 + g;
         uint4 o;
-        o.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
-        o.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
-        o.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
-        o.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+        o.x = pack_half2(pt[g * 8 + 0], pt[g * 8 + 1]);
+        o.y = pack_half2(pt[g * 8 + 2], pt[g * 8 + 3]);
+        o.z = pack_half2(pt[g * 8 + 4], pt[g * 8 + 5]);
+        o.w = pack_half2(pt[g * 8 + 6], pt[g * 8 + 7]);
         *reinterpret_cast<uint4*>(p_row + (chunk >> 3) * ATT_TILE + (((chunk & 7) ^ rx) << 4)) = o;
+        const int ic = chunk - ip_chunk0;          // chunk of the P_ip tile (keys ip_base + 8 ic ...)
+        if (p.n_ip > 0 && ic >= 0 && ic < 8) {
+          uint4 oi;
+          oi.x = pack_half2(pi[g * 8 + 0], pi[g * 8 + 1]);
+          oi.y = pack_half2(pi[g * 8 + 2], pi[g * 8 + 3]);
+          oi.z = pack_half2(pi[g * 8 + 4], pi[g * 8 + 5]);
+          oi.w = pack_half2(pi[g * 8 + 6], pi[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(pi_row + ((ic ^ rx) << 4)) = oi;
+        }
       }
     }
+    const float inv_t = 1.f / l_t;
+    const float inv_i = (p.n_ip > 0) ? p.ip_scale / l_i : 0.f;
     tc_fence_before();
     fence_proxy_async_smem();
     __syncwarp();
@@ -478,19 +487,26 @@ __global__ void __launch_bounds__(AX_THREADS, 3) attnx_f16_kernel(const __grid_c
     tc_fence_after();
     const int qrow = q0 + r;
     __half* dst = p.out + ((long long)b * p.Nq + qrow) * p.ldo + head * 64;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      uint32_t ov[32];
+      uint32_t ov[32], oi[32];
       tmem_ld_32x32b_x32(tS + c * 32, ov);
+      if (p.n_ip > 0) tmem_ld_32x32b_x32(tS + 64 + c * 32, oi);
       tmem_ld_wait();
       if (qrow < p.Nq) {
+        float y[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          y[e] = __uint_as_float(ov[e]) * inv_t;
+          if (p.n_ip > 0) y[e] = fmaf(__uint_as_float(oi[e]), inv_i, y[e]);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o;
-          o.x = pack_half2(__uint_as_float(ov[g * 8 + 0]), __uint_as_float(ov[g * 8 + 1]));
-          o.y = pack_half2(__uint_as_float(ov[g * 8 + 2]), __uint_as_float(ov[g * 8 + 3]));
-          o.z = pack_half2(__uint_as_float(ov[g * 8 + 4]), __uint_as_float(ov[g * 8 + 5]));
-          o.w = pack_half2(__uint_as_float(ov[g * 8 + 6]), __uint_as_float(ov[g * 8 + 7]));
+          o.x = pack_half2(y[g * 8 + 0], y[g * 8 + 1]);
+          o.y = pack_half2(y[g * 8 + 2], y[g * 8 + 3]);
+          o.z = pack_half2(y[g * 8 + 4], y[g * 8 + 5]);
+          o.w = pack_half2(y[g * 8 + 6], y[g * 8 + 7]);
           *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
         }
       }
@@ -1110,10 +1126,13 @@ extern "C" int ih_attention_ws_f16(const void* q, long long ldq, const void* k, 
     const int n_split_ctas = (pairs - p.n_whole) * p.split;
     p.ws_o = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + A2_CNT_BYTES);
     p.ws_ml = p.ws_o + (long long)n_split_ctas * 256 * 64;
-    // IH_ATTN_FUSED_MERGE=0: merge the parts with a second launch (attn_combine_kernel) instead of in-kernel
+    // IH_ATTN_FUSED_MERGE=1: the last part of a pair to finish merges all parts inside attn2_f16_kernel instead of the
+    // attn_combine_kernel launch.  Measured on B200 (profiles/r2_notes.md): correct but SLOWER -- one SM pulls the 0.5 MB
+    // of partials of a pair through its own L2 port (self-attention family 3.36 -> 5.28 ms per step) while the merge
+    // kernel spreads a pair over four blocks -- so the separate launch stays the default.
     static const bool fused_merge = [] {
       const char* e = getenv("IH_ATTN_FUSED_MERGE");
-      return !(e && e[0] == '0');
+      return e && e[0] == '1';
     }();
     p.ws_cnt = (fused_merge && n_split_ctas > 0 && pairs - p.n_whole <= A2_CNT_BYTES / (int)sizeof(int))
                    ? reinterpret_cast<int*>(workspace) : nullptr;

@@ -395,6 +395,37 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         for (int sl = 0; sl < SLABS; ++sl)
           if (n0 + sl * 64 < p.N) last_slab = sl;
       bool arrived = false;
+      constexpr bool kOneBarrier = (NBUF == SLABS);
+      // after the slab is complete in shared memory (barrier): the issuer stores it; one half-group computes the row
+      // statistics of exactly the fp16 values a later LayerNorm would read -- the whole 64-column row of the slab (both
+      // column halves), re-read from the staging buffer; one writer per (slab, row) slot
+      auto finish_slab = [&](int sl) {
+        const int col0 = n0 + sl * 64;
+        uint8_t* sbuf = stg + (sl % NBUF) * S::SLAB_BYTES;
+        if (issuer) {
+          if (p.mode == 0) tma_store_2d(&omap, sbuf, col0, m_tile * BM);
+          else tma_store_4d(&omap, sbuf, col0, x0, y0, img);
+          tma_store_commit();
+        }
+        if (p.stats_out && half == (sl & 1) && orow < p.M) {
+          const uint8_t* row_ptr = sbuf + r * 128;
+          float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (col0 + c * 8 < p.N) {
+              const uint4 o = *reinterpret_cast<const uint4*>(row_ptr + ((c ^ rx) << 4));
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_half2(ow[e]);
+                st_sum += f.x + f.y;
+                st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+              }
+            }
+          }
+          reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
+        }
+      };
 #pragma unroll 1
       for (int sl = 0; sl <= last_slab; ++sl) {
         const int col0 = n0 + sl * 64;
@@ -509,33 +540,20 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           o.w = pack_half2(x[6], x[7]);
           *slot = o;
         }
+        if (issuer && it == 0 && sl == 0) stamp(10);
+        if (!kOneBarrier) {
+          fence_proxy_async_smem();
+          named_bar_sync(3, GEMM_EPI_WARPS * 32);      // the slab is complete in shared memory
+          if (issuer && it == 0) stamp(sl == last_slab ? 12 : 11);
+          finish_slab(sl);
+        }
+      }
+      if (kOneBarrier && last_slab >= 0) {
+        // every slab has its own staging buffer: ONE proxy fence + ONE barrier for the whole tile, then all stores
         fence_proxy_async_smem();
-        named_bar_sync(3, GEMM_EPI_WARPS * 32);        // the slab is complete in shared memory
-        if (issuer && it == 0) stamp(sl == last_slab ? 12 : (sl == 0 ? 10 : 11));
-        if (issuer) {
-          if (p.mode == 0) tma_store_2d(&omap, sbuf, col0, m_tile * BM);
-          else tma_store_4d(&omap, sbuf, col0, x0, y0, img);
-          tma_store_commit();
-        }
-        if (p.stats_out && half == (sl & 1) && orow < p.M) {
-          // row statistics of exactly the fp16 values a later LayerNorm would read: my whole 64-column row of the slab
-          // (both column halves), re-read from the staging buffer; one writer per (slab, row) slot
-          float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (col0 + c * 8 < p.N) {
-              const uint4 o = *reinterpret_cast<const uint4*>(my_row + ((c ^ rx) << 4));
-              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_half2(ow[e]);
-                st_sum += f.x + f.y;
-                st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
-              }
-            }
-          }
-          reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
-        }
+        named_bar_sync(3, GEMM_EPI_WARPS * 32);
+        if (issuer && it == 0) stamp(12);
+        for (int sl = 0; sl <= last_slab; ++sl) finish_slab(sl);
       }
       if (!arrived) {   // no live slab in the tile (dead half tile of a CTA pair): still release the accumulator
         tc_fence_before();

@@ -88,9 +88,9 @@ int ih_attention_f16(const void* q, long long ldq, const void* k, long long ldk,
 
 /* ih_attention_f16 with a caller-owned scratch buffer (>= ih_attention_workspace_bytes(...) bytes, ZERO-FILLED once
  * by the caller; the kernels leave its arrival counters at zero).  With it the long self-attention shapes (Nk > 96,
- * n_ip == 0) cut the query tiles that would otherwise form a nearly empty last wave into KV parts that share one wave;
- * the last part of a tile to finish merges all partials inside the same kernel (flash-decoding style, fixed merge
- * order: deterministic, no second launch).  workspace == NULL behaves like ih_attention_f16. */
+ * n_ip == 0) cut the query tiles that would otherwise form a nearly empty last wave into KV parts that share one wave
+ * and are merged by a second small kernel (flash-decoding style, fixed merge order: deterministic; IH_ATTN_FUSED_MERGE=1
+ * merges inside the attention kernel instead, which measured slower).  workspace == NULL behaves like ih_attention_f16. */
 long long ih_attention_workspace_bytes(int B, int H, int Nq, int Nk, int n_ip);
 /* Fused front half of a cross-attention layer: out = CrossAttn(LayerNorm(h) Wq^T, k, v) for short key axes (Nk <= 96,
  * Nq % 128 == 0): the q projection (K input channels -> H*64) runs as a tcgen05 GEMM whose epilogue performs the
