@@ -463,6 +463,31 @@ def gpu_eager_baseline(cfg, lat: int, n: int, iters: int = 5):
     return out
 
 
+def build_clip_judge(device):
+    """The PNS judge north_star names ("allgather of CLIP scores"): candidate latents -> native VAE decoder -> device-side
+    resize / normalise / patchify -> ViT-bigG/14 vision tower -> cosine with the bigG text embedding of the prompt.  Real
+    architectures (SDXL VAE, OpenCLIP bigG towers), random-init weights generated on the GPU, identical on every rank."""
+    from imagharmony_b200.clip import ClipScorer, ClipTextTower, ClipTowerConfig, ClipVisionTower, tower_param_shapes
+    from imagharmony_b200.config import SDXL_VAE
+    from imagharmony_b200.vae import AutoencoderKLDecoder
+    from imagharmony_b200.weights import random_state_dict, shapes_of
+    vcfg = ClipTowerConfig(hidden_size=1664, intermediate_size=8192, num_hidden_layers=48, num_attention_heads=16,
+                           hidden_act="gelu", projection_dim=1280, image_size=224, patch_size=14)
+    tcfg = ClipTowerConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20,
+                           hidden_act="gelu", projection_dim=1280, vocab_size=49408, eos_token_id=49407)
+    vision = ClipVisionTower(vcfg, random_state_dict(tower_param_shapes(vcfg, "vision"), 31, device=device), device=device)
+    text = ClipTextTower(tcfg, random_state_dict(tower_param_shapes(tcfg, "text"), 32, device=device), device=device)
+    with torch.device("meta"):
+        vshapes = shapes_of(AutoencoderKLDecoder(SDXL_VAE))
+    vae = AutoencoderKLDecoder.from_state_dict(SDXL_VAE, random_state_dict(vshapes, 33, device=device), device=device)
+    scorer = ClipScorer(vision, text, decode=vae.decode)
+    ids = torch.full((1, 77), 49407, dtype=torch.int64)
+    ids[0, 0] = 49406
+    ids[0, 1:9] = torch.tensor([320, 1125, 539, 5567, 15, 2533, 3027, 267])      # a fixed synthetic prompt (no vocabulary offline)
+    scorer.set_prompt(input_ids=ids)
+    return scorer
+
+
 def pns_block(args, eng, cfg, lat, K, rank, world, device, dist, single_step_ms):
     """BASELINE config 4 shape at this world size: 4 candidate noises per GPU, K steps each, one batch per rank:
     H2D -> K graph replays -> score -> all_gather -> argmax -> winner broadcast; wall clock, max over ranks."""
@@ -481,8 +506,9 @@ def pns_block(args, eng, cfg, lat, K, rank, world, device, dist, single_step_ms)
                           for s in batch_seeds]) * ins
         return eng.run(lat0.half().pin_memory(), rep(pos1, b), rep(neg1, b), rep(pooled1, b), rep(npooled1, b),
                        rep(tid1, b), K, guidance_scale=5.0, ip_scale=1.0)
-    scorer = LinearProbeScorer(4 * lat * lat, seed=99, device=device)
+    scorer = build_clip_judge(device) if args.pns_judge == "clip" else LinearProbeScorer(4 * lat * lat, seed=99, device=device)
     eng.run(*[t.pin_memory() for t in synth_inputs(cfg, per, lat, K, rank)], K, stop_after=2)     # capture batch-8 graph
+    scorer(torch.zeros((per, 4, lat, lat), dtype=torch.float16, device=device))                   # warm the judge
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -573,6 +599,9 @@ def main():
     ap.add_argument("--pns", type=int, default=0,
                     help="PNS mode: N candidate noises in total, sharded over the ranks (BASELINE config 4: N=32 on 8 GPUs)")
     ap.add_argument("--pns-batch", type=int, default=4, help="candidates denoised together per rank (UNet batch 2x)")
+    ap.add_argument("--pns-judge", default="clip", choices=["clip", "probe"],
+                    help="judge of the N > 1 `pns` block: native CLIP image-text cosine on decoded candidates (random-init "
+                         "bigG towers + SDXL VAE) or the synthetic linear probe of the latent")
     ap.add_argument("--pns-preview", type=int, default=0,
                     help="two-phase PNS: preview steps per candidate before the judge; the winner alone runs the rest")
     args = ap.parse_args()

@@ -67,6 +67,42 @@ class ClipTowerConfig:
         return cls(**kw)
 
 
+def tower_param_shapes(cfg: "ClipTowerConfig", kind: str) -> Dict[str, tuple]:
+    """{transformers state-dict key: shape} of a CLIP text (`kind="text"`) or vision tower with projection head -- what
+    `ClipTextTower` / `ClipVisionTower` consume; lets benchmarks build random-init towers straight on the GPU (no weights
+    exist offline, and constructing a 1.8 B parameter `transformers` module on the host takes a minute)."""
+    C, F, P = cfg.hidden_size, cfg.intermediate_size, cfg.projection_dim
+    pre = "text_model." if kind == "text" else "vision_model."
+    sh: Dict[str, tuple] = {}
+    if kind == "text":
+        sh[pre + "embeddings.token_embedding.weight"] = (cfg.vocab_size, C)
+        sh[pre + "embeddings.position_embedding.weight"] = (cfg.max_position_embeddings, C)
+    else:
+        g = cfg.image_size // cfg.patch_size
+        sh[pre + "embeddings.class_embedding"] = (C,)
+        sh[pre + "embeddings.patch_embedding.weight"] = (C, cfg.num_channels, cfg.patch_size, cfg.patch_size)
+        sh[pre + "embeddings.position_embedding.weight"] = (g * g + 1, C)
+        sh[pre + "pre_layrnorm.weight"] = sh[pre + "pre_layrnorm.bias"] = (C,)
+    for i in range(cfg.num_hidden_layers):
+        p = f"{pre}encoder.layers.{i}."
+        for n in "qkv":
+            sh[p + f"self_attn.{n}_proj.weight"], sh[p + f"self_attn.{n}_proj.bias"] = (C, C), (C,)
+        sh[p + "self_attn.out_proj.weight"], sh[p + "self_attn.out_proj.bias"] = (C, C), (C,)
+        sh[p + "layer_norm1.weight"] = sh[p + "layer_norm1.bias"] = (C,)
+        sh[p + "layer_norm2.weight"] = sh[p + "layer_norm2.bias"] = (C,)
+        sh[p + "mlp.fc1.weight"], sh[p + "mlp.fc1.bias"] = (F, C), (F,)
+        sh[p + "mlp.fc2.weight"], sh[p + "mlp.fc2.bias"] = (C, F), (C,)
+    if kind == "text":
+        sh[pre + "final_layer_norm.weight"] = sh[pre + "final_layer_norm.bias"] = (C,)
+        if P:
+            sh["text_projection.weight"] = (P, C)
+    else:
+        sh[pre + "post_layernorm.weight"] = sh[pre + "post_layernorm.bias"] = (C,)
+        if P:
+            sh["visual_projection.weight"] = (P, C)
+    return sh
+
+
 class _Layer:
     __slots__ = ("ln1", "ln2", "w_qkv", "b_qkv", "w_o", "b_o", "w_fc1", "b_fc1", "w_fc2", "b_fc2")
 

@@ -426,10 +426,41 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
         }
       };
-      // residual wait (slab already fetched into its staging buffer) + arithmetic + fp16 row segment into the staging slab
-      auto process_slab = [&](int sl, const uint32_t (&v)[32], const uint32_t (&g)[32]) {
+#pragma unroll 1
+      for (int sl = 0; sl <= last_slab; ++sl) {
+        const int col0 = n0 + sl * 64;
         const int buf = sl % NBUF;
-        uint8_t* my_row = stg + buf * S::SLAB_BYTES + r * 128;
+        uint8_t* sbuf = stg + buf * S::SLAB_BYTES;
+        uint8_t* my_row = sbuf + r * 128;
+        uint32_t v[32];
+        uint32_t g[32];
+        tmem_ld_32x32b_x32(taddr + sl * 64, v);
+        if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g);
+        if (sl >= NBUF) {
+          // staging-buffer reuse (BN = 256 only): the store of slab sl - NBUF must have read the buffer out; then the
+          // residual slab is fetched into it
+          if (issuer) {
+            tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
+            if (p.residual) {
+              mbar_arrive_expect_tx(&res_bar[buf], BM * 128);
+              if (p.mode == 0) tma_load_2d(sbuf, &rmap, &res_bar[buf], col0, m_tile * BM);
+              else tma_load_4d(sbuf, &rmap, &res_bar[buf], col0, x0, y0, img);
+            }
+          }
+          named_bar_sync(2, GEMM_EPI_WARPS * 32);
+        }
+        tmem_ld_wait();
+        if (issuer && it == 0 && sl == 0) stamp(9);
+        if (sl == last_slab) {
+          // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
+          arrived = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
         if (p.residual) {
           mbar_wait(&res_bar[buf], (res_par >> buf) & 1u);
           res_par ^= 1u << buf;
@@ -509,72 +540,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           o.w = pack_half2(x[6], x[7]);
           *slot = o;
         }
-      };
-      if constexpr (kOneBarrier) {
-        // every slab has its own staging buffer: all TMEM loads are issued at once, the accumulator is released, then
-        // the slabs' arithmetic is one straight-line region (independent work for the scheduler to interleave), ONE
-        // proxy fence + ONE barrier for the tile, then all stores
-        uint32_t v[SLABS][32];
-        uint32_t g[GEGLU ? SLABS : 1][32];
-#pragma unroll
-        for (int sl = 0; sl < SLABS; ++sl)
-          if (sl <= last_slab) {
-            tmem_ld_32x32b_x32(taddr + sl * 64, v[sl]);
-            if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g[GEGLU ? sl : 0]);
-          }
-        tmem_ld_wait();
-        if (issuer && it == 0) stamp(9);
-        if (last_slab >= 0) {
-          // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
-          arrived = true;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
-            else mbar_arrive(&tmem_empty_bar[acc]);
-          }
-        }
-#pragma unroll
-        for (int sl = 0; sl < SLABS; ++sl)
-          if (sl <= last_slab) process_slab(sl, v[sl], g[GEGLU ? sl : 0]);
-        if (issuer && it == 0) stamp(10);
-      } else {
-#pragma unroll 1
-        for (int sl = 0; sl <= last_slab; ++sl) {
-          const int col0 = n0 + sl * 64;
-          const int buf = sl % NBUF;
-          uint8_t* sbuf = stg + buf * S::SLAB_BYTES;
-          uint32_t v[32];
-          uint32_t g[32];
-          tmem_ld_32x32b_x32(taddr + sl * 64, v);
-          if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g);
-          if (sl >= NBUF) {
-            // staging-buffer reuse (BN = 256 only): the store of slab sl - NBUF must have read the buffer out; then the
-            // residual slab is fetched into it
-            if (issuer) {
-              tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
-              if (p.residual) {
-                mbar_arrive_expect_tx(&res_bar[buf], BM * 128);
-                if (p.mode == 0) tma_load_2d(sbuf, &rmap, &res_bar[buf], col0, m_tile * BM);
-                else tma_load_4d(sbuf, &rmap, &res_bar[buf], col0, x0, y0, img);
-              }
-            }
-            named_bar_sync(2, GEMM_EPI_WARPS * 32);
-          }
-          tmem_ld_wait();
-          if (issuer && it == 0 && sl == 0) stamp(9);
-          if (sl == last_slab) {
-            // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
-            arrived = true;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
-              else mbar_arrive(&tmem_empty_bar[acc]);
-            }
-          }
-          process_slab(sl, v, g);
-          if (issuer && it == 0 && sl == 0) stamp(10);
+        if (issuer && it == 0 && sl == 0) stamp(10);
+        if (!kOneBarrier) {
           fence_proxy_async_smem();
           named_bar_sync(3, GEMM_EPI_WARPS * 32);      // the slab is complete in shared memory
           if (issuer && it == 0) stamp(sl == last_slab ? 12 : 11);

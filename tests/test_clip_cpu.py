@@ -98,3 +98,16 @@ def test_resize_patchify_ref_is_identity_resize_at_equal_size():
     rows = resize_patchify_ref(img, 28, 14, 592, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))       # (v - .5) / .5 undoes [-1,1] -> [0,1]
     back = rows[:, :588].reshape(1, 2, 2, 3, 14, 14).permute(0, 3, 1, 4, 2, 5).reshape(1, 3, 28, 28)
     assert torch.allclose(back, img, atol=1e-6) and torch.count_nonzero(rows[:, 588:]) == 0
+
+
+def test_tower_param_shapes_match_transformers_keys():
+    """The key / shape table used to build random-init towers on the GPU (bench.py's CLIP judge) is the transformers one."""
+    from imagharmony_b200.clip import ClipTowerConfig, tower_param_shapes
+    from oracle.clip_ref import hf_text_model, hf_vision_model
+    ht = hf_text_model(1, True, vocab_size=100, eos_token_id=99, hidden_size=64, intermediate_size=96,
+                       num_hidden_layers=2, num_attention_heads=2, hidden_act="gelu", projection_dim=32)
+    hv = hf_vision_model(1, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=2,
+                         hidden_act="gelu", projection_dim=32, image_size=56, patch_size=14)
+    for hf, kind in ((ht, "text"), (hv, "vision")):
+        want = {k: tuple(v.shape) for k, v in hf.state_dict().items() if "position_ids" not in k}
+        assert tower_param_shapes(ClipTowerConfig.from_hf(hf.config), kind) == want
