@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/ih_api.h"
 #include "host_util.h"
 #include "ptx.cuh"
@@ -426,45 +428,12 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           reinterpret_cast<float2*>(p.stats_out)[(long long)(col0 >> 6) * p.M + orow] = make_float2(st_sum, st_sq);
         }
       };
-#pragma unroll 1
-      for (int sl = 0; sl <= last_slab; ++sl) {
-        const int col0 = n0 + sl * 64;
-        const int buf = sl % NBUF;
-        uint8_t* sbuf = stg + buf * S::SLAB_BYTES;
-        uint8_t* my_row = sbuf + r * 128;
-        uint32_t v[32];
-        uint32_t g[32];
-        tmem_ld_32x32b_x32(taddr + sl * 64, v);
-        if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g);
-        if (sl >= NBUF) {
-          // staging-buffer reuse (BN = 256 only): the store of slab sl - NBUF must have read the buffer out; then the
-          // residual slab is fetched into it
-          if (issuer) {
-            tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
-            if (p.residual) {
-              mbar_arrive_expect_tx(&res_bar[buf], BM * 128);
-              if (p.mode == 0) tma_load_2d(sbuf, &rmap, &res_bar[buf], col0, m_tile * BM);
-              else tma_load_4d(sbuf, &rmap, &res_bar[buf], col0, x0, y0, img);
-            }
-          }
-          named_bar_sync(2, GEMM_EPI_WARPS * 32);
-        }
-        tmem_ld_wait();
-        if (issuer && it == 0 && sl == 0) stamp(9);
-        if (sl == last_slab) {
-          // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
-          arrived = true;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
-            else mbar_arrive(&tmem_empty_bar[acc]);
-          }
-        }
-        if (p.residual) {
-          mbar_wait(&res_bar[buf], (res_par >> buf) & 1u);
-          res_par ^= 1u << buf;
-        }
+      const uint32_t sbias_u32 = smem_u32(sBias);
+      // arithmetic of one slab: registers (this thread's 32 accumulator columns) -> fp16 row segment in the staging slab.
+      // `with_act` is a compile-time tag: the UNet's GEMMs have no activation, so they run a lean instruction stream (the
+      // epilogue is latency-bound: two warps per scheduler, one dependent chain each)
+      auto slab_math = [&](auto with_act, int sl, const uint32_t (&v)[32], const uint32_t (&g)[32]) {
+        uint8_t* my_row = stg + (sl % NBUF) * S::SLAB_BYTES + r * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const int j = half * 4 + j4;             // 16-byte chunk of the 64-column slab row
@@ -473,7 +442,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           {
             // acc * rstd + bias: rstd = alpha without a folded LayerNorm; with one, `bias` carries W beta + b and the
             // weight rows are gamma-scaled AND centred, so the mean term has already cancelled inside the MMA
-            const uint4 bv = *reinterpret_cast<const uint4*>(sBias + lc);
+            const uint4 bv = lds128(sbias_u32 + lc * 2);
             const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -484,7 +453,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           }
           if (GEGLU) {
             float gt[8];
-            const uint4 gv = *reinterpret_cast<const uint4*>(sBias + BN / 2 + lc);
+            const uint4 gv = lds128(sbias_u32 + (BN / 2 + lc) * 2);
             const uint32_t bw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -498,7 +467,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           if (rb) {
             uint4 rv;
             if (rb_uniform) {
-              rv = *reinterpret_cast<const uint4*>(sRowb + lc);
+              rv = lds128(sbias_u32 + (BN + lc) * 2);
             } else {   // rows of several groups in one tile (not used by the UNet): per-row global loads
               int col = n0 + lc;
               if (col > p.N - 8) col = p.N - 8;
@@ -512,15 +481,17 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
               x[2 * e + 1] += f.y;
             }
           }
-          if (p.act == 1) {
+          if constexpr (decltype(with_act)::value) {
+            if (p.act == 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
-          } else if (p.act == 2) {
+              for (int e = 0; e < 8; ++e) x[e] = silu_f(x[e]);
+            } else if (p.act == 2) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
-          } else if (p.act == 3) {   // quick_gelu x * sigmoid(1.702 x) ([3P] CLIP-L text tower MLP)
+              for (int e = 0; e < 8; ++e) x[e] = gelu_erf_f(x[e]);
+            } else if (p.act == 3) {   // quick_gelu x * sigmoid(1.702 x) ([3P] CLIP-L text tower MLP)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __fdividef(x[e], 1.f + __expf(-1.702f * x[e]));
+              for (int e = 0; e < 8; ++e) x[e] = __fdividef(x[e], 1.f + __expf(-1.702f * x[e]));
+            }
           }
           uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ rx) << 4));
           if (p.residual) {
@@ -540,12 +511,81 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           o.w = pack_half2(x[6], x[7]);
           *slot = o;
         }
+      };
+      // staging-buffer reuse (BN = 256 without GEGLU only): the store of slab sl - NBUF must have read the buffer out; then
+      // the residual slab is fetched into it
+      auto reuse_buffer = [&](int sl) {
+        const int col0 = n0 + sl * 64;
+        const int buf = sl % NBUF;
+        uint8_t* sbuf = stg + buf * S::SLAB_BYTES;
+        if (issuer) {
+          tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
+          if (p.residual) {
+            mbar_arrive_expect_tx(&res_bar[buf], BM * 128);
+            if (p.mode == 0) tma_load_2d(sbuf, &rmap, &res_bar[buf], col0, m_tile * BM);
+            else tma_load_4d(sbuf, &rmap, &res_bar[buf], col0, x0, y0, img);
+          }
+        }
+        named_bar_sync(2, GEMM_EPI_WARPS * 32);
+      };
+      auto release_accumulator = [&]() {
+        // this warp's last TMEM read of the accumulator is complete: hand the buffer back to the MMA warp
+        arrived = true;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
+      };
+      auto wait_residual = [&](int sl) {
+        if (p.residual) {
+          const int buf = sl % NBUF;
+          mbar_wait(&res_bar[buf], (res_par >> buf) & 1u);
+          res_par ^= 1u << buf;
+        }
+      };
+      auto slab_done = [&](int sl) {
         if (issuer && it == 0 && sl == 0) stamp(10);
         if (!kOneBarrier) {
           fence_proxy_async_smem();
           named_bar_sync(3, GEMM_EPI_WARPS * 32);      // the slab is complete in shared memory
           if (issuer && it == 0) stamp(sl == last_slab ? 12 : 11);
           finish_slab(sl);
+        }
+      };
+      if (!GEGLU && p.act == 0) {
+        // fast path (every GEMM / conv of the UNet except the FF GEGLU-in): no activation code, and the TMEM load of
+        // slab sl + 1 is in flight during the arithmetic of slab sl (two register buffers)
+        uint32_t v[2][32];
+        if (last_slab >= 0) tmem_ld_32x32b_x32(taddr, v[0]);
+#pragma unroll
+        for (int sl = 0; sl < SLABS; ++sl) {
+          if (sl <= last_slab) {
+            if (sl >= NBUF) reuse_buffer(sl);
+            tmem_ld_wait();
+            if (issuer && it == 0 && sl == 0) stamp(9);
+            if (sl + 1 < SLABS && sl + 1 <= last_slab) tmem_ld_32x32b_x32(taddr + (sl + 1) * 64, v[(sl + 1) & 1]);
+            if (sl == last_slab) release_accumulator();
+            wait_residual(sl);
+            slab_math(std::false_type{}, sl, v[sl & 1], v[sl & 1]);
+            slab_done(sl);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int sl = 0; sl <= last_slab; ++sl) {
+          uint32_t v[32];
+          uint32_t g[32];
+          tmem_ld_32x32b_x32(taddr + sl * 64, v);
+          if (GEGLU) tmem_ld_32x32b_x32(taddr + BN / 2 + sl * 64, g);
+          if (sl >= NBUF) reuse_buffer(sl);
+          tmem_ld_wait();
+          if (issuer && it == 0 && sl == 0) stamp(9);
+          if (sl == last_slab) release_accumulator();
+          wait_residual(sl);
+          slab_math(std::true_type{}, sl, v, g);
+          slab_done(sl);
         }
       }
       if (kOneBarrier && last_slab >= 0) {

@@ -120,16 +120,16 @@ def pns_select(run_candidates: Callable[[List[int]], torch.Tensor], seeds: Seque
         if world == 1:
             best_lat = torch.cat(lat_parts)[off].clone()
         else:
-            shape = None
             if rank == owner:
-                best_lat = torch.cat(lat_parts)[off].contiguous().clone()
-                shape = torch.tensor(list(best_lat.shape), device=dev, dtype=torch.int64)
-            else:
-                shape = torch.zeros(3, device=dev, dtype=torch.int64)
-            dist.broadcast(shape, src=owner)
+                best_lat = torch.cat(lat_parts)[off].contiguous().clone().to(torch.float16)
+            if all(c > 0 for c in counts):
+                shape = tuple(lat_parts[0].shape[1:])      # every rank holds candidates of the same shape: no exchange
+            else:                                          # a rank without candidates must learn the latent shape
+                st = (torch.tensor(list(best_lat.shape), device=dev, dtype=torch.int64) if rank == owner
+                      else torch.zeros(3, device=dev, dtype=torch.int64))
+                dist.broadcast(st, src=owner)
+                shape = tuple(int(v) for v in st.tolist())
             if rank != owner:
-                best_lat = torch.empty(tuple(int(v) for v in shape.tolist()), dtype=torch.float16, device=dev)
-            else:
-                best_lat = best_lat.to(torch.float16)
+                best_lat = torch.empty(shape, dtype=torch.float16, device=dev)
             dist.broadcast(best_lat, src=owner)       # 128 KiB at 1024^2: latency-bound, NVLink irrelevant
     return PNSResult(scores=scores, best_index=best, best_seed=int(seeds[best]), best_latents=best_lat)

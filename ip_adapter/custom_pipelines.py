@@ -106,9 +106,19 @@ class StableDiffusionXLCustomPipeline:
         for name in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors"):
             vf = os.path.join(path, "vae", name)
             if os.path.exists(vf):
+                import dataclasses
+                import json
                 from imagharmony_b200.config import SDXL_VAE
                 from imagharmony_b200.vae import AutoencoderKLDecoder
-                vae = AutoencoderKLDecoder.from_state_dict(vae_cfg or SDXL_VAE, load_file(vf), device=device)  # decoder keys only
+                vcfg = vae_cfg or SDXL_VAE
+                cj = os.path.join(path, "vae", "config.json")
+                if vae_cfg is None and os.path.exists(cj):
+                    # `force_upcast` decides between the scaled residual stream (the reference's fp32 upcast,
+                    # custom_pipelines.py:366-371) and plain fp16 (fp16-fix checkpoints set it to false)
+                    meta = json.load(open(cj))
+                    vcfg = dataclasses.replace(vcfg, force_upcast=bool(meta.get("force_upcast", True)),
+                                               scaling_factor=float(meta.get("scaling_factor", vcfg.scaling_factor)))
+                vae = AutoencoderKLDecoder.from_state_dict(vcfg, load_file(vf), device=device)  # decoder keys only
                 break
         enc = None
         from .encoders import ClipPromptEncoder
