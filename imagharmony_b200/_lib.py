@@ -71,6 +71,7 @@ SIGNATURES = {
     "ih_conv2d_scaled_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p]),
     "ih_gemm_set_trace": (None, [c_void_p]),
+    "ih_gemm_prefetch_next": (None, [c_void_p, c_longlong]),
     "ih_conv2d_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ih_attention_f16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,

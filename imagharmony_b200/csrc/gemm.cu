@@ -55,6 +55,11 @@ struct GemmParams {
   long long ldo;
   int act;  // 0 none, 1 SiLU, 2 GELU(erf), 3 quick-GELU (applied after bias, before residual)
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA 0 (ih_gemm_set_trace), nullptr in production
+  // L2 prefetch of the NEXT kernel's weights (ih_gemm_prefetch_next): inside a denoise step every GEMM streams its weights
+  // from HBM (5.2 GB per step >> L2), and a launch of 5-25 us cannot hide the first HBM round trips.  An otherwise idle
+  // epilogue warp issues cp.async.bulk.prefetch.L2 for this CTA's slice while the main loop runs.
+  const unsigned char* pf_ptr;
+  unsigned long long pf_bytes;
   // LayerNorm folding (plain GEMM mode only).  A producer GEMM writes, per output row and 64-column slab, the sum and
   // the sum of squares of the fp16-rounded values it stores (stats_out [ceil(N/64), M, 2] fp32, one writer per slot:
   // deterministic, nothing to zero).  The consumer GEMM multiplies the RAW rows with gamma-scaled, row-CENTRED weights
@@ -303,6 +308,17 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
     __half* sBias = reinterpret_cast<__half*>(smem + S::BIAS_OFF);   // [BN]: columns of this tile (GEGLU: value | gate)
     __half* sRowb = sBias + BN;                                       // [BN_OUT]: row-bias row when uniform over the tile
     uint32_t res_par = 0;                 // bit b: parity of res_bar[b]
+    if (p.pf_ptr && ew == GEMM_EPI_WARPS - 1 && lane == 0) {
+      // my 1/gridDim slice of the next kernel's weights -> L2 (a hint: no completion to wait for)
+      constexpr unsigned long long CH = 16384;
+      const unsigned long long per = ((p.pf_bytes / gridDim.x) + CH - 1) / CH * CH;
+      unsigned long long off = per * blockIdx.x;
+      const unsigned long long end = off + per < p.pf_bytes ? off + per : p.pf_bytes;
+      for (; off < end; off += CH) {
+        const unsigned long long n = end - off < CH ? ((end - off) & ~15ull) : CH;
+        if (n) l2_prefetch_bulk(p.pf_ptr + off, (uint32_t)n);
+      }
+    }
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int n_tile = tile % n_tiles;
@@ -730,6 +746,15 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
 }
 
 static unsigned long long* g_trace = nullptr;
+// one-shot hint consumed by the next GEMM / conv launch of this thread (ih_gemm_prefetch_next)
+static thread_local const void* g_pf_ptr = nullptr;
+static thread_local unsigned long long g_pf_bytes = 0;
+static void take_prefetch_hint(GemmParams& p) {
+  p.pf_ptr = (const unsigned char*)g_pf_ptr;
+  p.pf_bytes = g_pf_bytes;
+  g_pf_ptr = nullptr;
+  g_pf_bytes = 0;
+}
 }  // namespace ih
 
 using namespace ih;
@@ -738,6 +763,11 @@ using namespace ih;
 // (0 kernel entry, 1 setup done, 2 predecessor finished, 3 first operands landed, 4..7 accumulator ready for tiles
 // 0..3+, 8 CTA done); pass NULL to disable.
 extern "C" void ih_gemm_set_trace(void* device_buffer) { ih::g_trace = (unsigned long long*)device_buffer; }
+
+extern "C" void ih_gemm_prefetch_next(const void* weights, long long bytes) {
+  ih::g_pf_ptr = (weights && bytes >= 16 && ((uintptr_t)weights & 15) == 0) ? weights : nullptr;
+  ih::g_pf_bytes = ih::g_pf_ptr ? (unsigned long long)bytes : 0;
+}
 
 static int gemm_impl(const void* a, long long lda, const void* w, const void* bias, const void* rowbias,
                      int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
@@ -804,6 +834,7 @@ static int gemm_impl(const void* a, long long lda, const void* w, const void* bi
   p.ldo = ldo;
   p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : ((epilogue & IH_EPI_QUICK_GELU) ? 3 : 0));
   p.trace = g_trace;
+  take_prefetch_hint(p);
   IH_CHECK(!ln_stats || ln_slabs > 0, IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_slabs > 0");
   IH_CHECK(!stats_out || N % 64 == 0 || geglu, IH_ERR_SHAPE, "ih_gemm_ln_f16: stats_out needs N %% 64 == 0");
   p.stats_out = (float*)stats_out;
@@ -888,6 +919,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
   p.out = (__half*)out;
   p.ldo = Cout;
   p.trace = g_trace;
+  take_prefetch_hint(p);
   p.alpha = alpha;
 
   TmapSet4 amaps;

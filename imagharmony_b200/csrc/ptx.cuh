@@ -408,6 +408,10 @@ __device__ __forceinline__ void bulk_store_linear(void* gdst, const void* ssrc, 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // wait until at most N of this thread's most recent bulk-store groups are still reading their shared-memory source
+// L2 prefetch of `bytes` (multiple of 16) global bytes at a 16-byte aligned address; a hint without completion tracking
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 // 16-byte shared-memory load by shared-window address (the generic-address form compiles to LD.E, which is slower)
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;

@@ -104,6 +104,15 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+PREFETCH_WEIGHTS = os.environ.get("IH_PREFETCH", "1") != "0"
+
+
+def prefetch_next(w: Optional[torch.Tensor]) -> None:
+    """Hint for the NEXT linear / conv3x3 call: while it runs, pull `w` (the weight of the launch after it) into L2."""
+    if PREFETCH_WEIGHTS and w is not None and w.is_cuda:
+        _lib.load().ih_gemm_prefetch_next(w.data_ptr(), w.numel() * w.element_size())
+
+
 def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
     """LayerNorm(x) @ w.T + bias == rstd(x) * (x @ w_c.T) + c with
        w_c[n, k] = w[n, k] gamma[k] - mean_k(w[n, :] gamma)   (rows centred: x @ w_c.T = (x - mean(x)) @ (w gamma).T)

@@ -47,6 +47,7 @@ class Attention(nn.Module):
         self._w_qkv = None
         self._w_kv = None
         self._ln = None      # (gamma-scaled centred weight, constant vector) of the projection that consumes a folded LayerNorm
+        self._next_w = None  # weight of the GEMM that runs after this attention's out projection (L2 prefetch hint)
 
     def fold_ln(self, norm: nn.LayerNorm) -> None:
         """Fold the block's LayerNorm into the first projection of this attention (q|k|v for attn1, q for attn2)."""
@@ -68,6 +69,13 @@ class Attention(nn.Module):
         self._w_qkv = None
         self._w_kv = None
         self._ln = None
+        self._next_w = None
+
+    def first_weight(self) -> torch.Tensor:
+        """The weight the first GEMM of this attention streams (folded-LayerNorm form when it exists)."""
+        if self._ln is not None:
+            return self._ln[0]
+        return self.to_q.weight.detach() if self.is_cross else self.fused_qkv_weight()   # detach: never register as a parameter
 
     def forward(self, hidden_states, encoder_hidden_states=None, **fused):
         """`fused` carries the native-processor extensions (residual=, ln_stats=, ln_eps=, stats_out=)."""
@@ -99,6 +107,7 @@ class ResnetBlock2D(nn.Module):
         B, H, W, _ = x.shape
         h = ops.groupnorm(x, self.norm1.weight, self.norm1.bias, x1=skip, groups=self.groups, eps=1e-5, silu=True)
         temb = temb_all[:, self.temb_offset:self.temb_offset + self.cout]
+        ops.prefetch_next(self._w2)
         h = ops.conv3x3(h, self._w1, self.conv1.bias, rowbias=temb)
         h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=1e-5, silu=True)
         if self.conv_shortcut is not None:
@@ -134,12 +143,16 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim)
         self._ln_ff = None
+        self._next_w = None       # weight of the GEMM after this block's FF-out (next block's q|k|v, or proj_out)
 
     def finalize(self):
         self.attn1.fold_ln(self.norm1)
         self.attn2.fold_ln(self.norm2)
         self._ln_ff = ops.fold_layernorm(self.ff.net[0].proj.weight.detach(), self.ff.net[0].proj.bias.detach(),
                                          self.norm3.weight.detach(), self.norm3.bias.detach())
+        # L2 prefetch chain inside the block: attn1.out -> attn2 q weight, attn2.out -> GEGLU weight
+        self.attn1._next_w = self.attn2.first_weight()
+        self.attn2._next_w = self._ln_ff[0]
 
     def _attend(self, attn, norm, h, ehs, h_stats, want_stats):
         """h + attn(norm(h)) with the LayerNorm folded into the attention's first GEMM when row statistics of `h`
@@ -164,6 +177,7 @@ class BasicTransformerBlock(nn.Module):
         h, st = self._attend(self.attn1, self.norm1, h, None, h_stats if fold else None, fold)
         h, st = self._attend(self.attn2, self.norm2, h, ehs, st, fold)
         h2d = h.reshape(B * N, C)
+        ops.prefetch_next(self.ff.net[2].weight)
         if st is not None and self._ln_ff is not None:
             w_c, c = self._ln_ff
             g = ops.linear(h2d, w_c, c, geglu=True, ln=(st, self.norm3.eps))
@@ -171,6 +185,7 @@ class BasicTransformerBlock(nn.Module):
             n = ops.layernorm(h, self.norm3.weight, self.norm3.bias, self.norm3.eps)
             g = ops.linear(n.reshape(B * N, C), self.ff.net[0].proj.weight, self.ff.net[0].proj.bias, geglu=True)
         st_out = torch.empty((C // 64, B * N, 2), dtype=torch.float32, device=h.device) if (fold and want_stats) else None
+        ops.prefetch_next(self._next_w)
         h2 = ops.linear(g, self.ff.net[2].weight, self.ff.net[2].bias, residual=h2d, stats_out=st_out)
         return h2.reshape(B, N, C), st_out
 
@@ -184,10 +199,17 @@ class Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, cross_dim) for _ in range(depth)])
         self.proj_out = nn.Linear(dim, dim)
 
+    def link_prefetch(self):
+        """FF-out of block i hints block i + 1's first weight (the last block hints proj_out); proj_in hints block 0."""
+        blocks = list(self.transformer_blocks)
+        for i, blk in enumerate(blocks):
+            blk._next_w = blocks[i + 1].attn1.first_weight() if i + 1 < len(blocks) else self.proj_out.weight.detach()
+
     def forward(self, x: torch.Tensor, ehs: torch.Tensor) -> torch.Tensor:
         B, H, W, C = x.shape
         h = ops.groupnorm(x, self.norm.weight, self.norm.bias, groups=self.groups, eps=1e-6, silu=False)
         st = torch.empty((C // 64, B * H * W, 2), dtype=torch.float32, device=x.device) if C % 64 == 0 else None
+        ops.prefetch_next(self.transformer_blocks[0].attn1.first_weight())
         h = ops.linear(h.reshape(B * H * W, C), self.proj_in.weight, self.proj_in.bias, stats_out=st)
         h = h.reshape(B, H * W, C)
         nblk = len(self.transformer_blocks)
@@ -395,6 +417,9 @@ class UNet2DConditionModel(nn.Module):
         for m in self.modules():      # after the fused q|k|v weights exist: fold the LayerNorms into their consumers
             if isinstance(m, BasicTransformerBlock):
                 m.finalize()
+        for m in self.modules():
+            if isinstance(m, Transformer2DModel):
+                m.link_prefetch()
         self._w_temb = torch.cat(ws, 0).contiguous()
         self._b_temb = torch.cat(bs, 0).contiguous()
         # the 4-channel ends run on the tensor-core GEMM: conv_in weight flattened [320, 36] -> [320, 64] (zero pad);

@@ -61,6 +61,12 @@ int ih_gemm_scaled_f16(const void* a, long long lda, const void* w, const void* 
                        long long ldr, void* out, long long ldo, int M, int N, int K, int epilogue, float alpha,
                        void* stream);
 
+/* One-shot hint for the NEXT ih_gemm_* / ih_conv2d_* launch of the calling thread: while it runs, an idle warp of every
+ * CTA prefetches a slice of `weights` (the weight matrix of the kernel that will follow it) into L2
+ * (cp.async.bulk.prefetch.L2).  Inside a denoise step every layer's weights come from HBM; this hides the first round
+ * trips of the following launch.  A pure performance hint: results never depend on it. */
+void ih_gemm_prefetch_next(const void* weights, long long bytes);
+
 /* Debug aid: CTA 0 of later GEMM / conv launches writes %globaltimer stamps into this device buffer (>= 16 uint64);
  * NULL disables.  Not used on the product path. */
 void ih_gemm_set_trace(void* device_buffer);

@@ -47,6 +47,7 @@ def _cross_attention(attn, x, kv, B, N, Nk, C, *, n_ip=0, ip_scale=1.0, ln_stats
     if ops.USE_FUSED_XATTN and not need_q and ops.xattn_q_fused_ok(N, Nk):
         return None, ops.xattn_q_fused(x, w, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip, ip_scale=ip_scale,
                                        bias=bias, ln=ln)
+    ops.prefetch_next(attn.to_out[0].weight)                      # L2 hint: the out projection follows the attention
     q = ops.linear(x, w, bias, ln=ln)
     return q, ops.attention(q, kv[:, :C], kv[:, C:], B, attn.heads, N, Nk, n_ip=n_ip, ip_scale=ip_scale)
 
@@ -73,6 +74,7 @@ class AttnProcessor2_0(torch.nn.Module):
         H = attn.heads
         x = hidden_states.reshape(B * N, C)
         if encoder_hidden_states is None:
+            ops.prefetch_next(attn.to_out[0].weight)                              # L2 hint for the launch after q|k|v
             if ln_stats is not None:
                 w_c, c = attn._ln
                 qkv = ops.linear(x, w_c, c, ln=(ln_stats, ln_eps))                # LayerNorm folded into q|k|v
@@ -84,6 +86,7 @@ class AttnProcessor2_0(torch.nn.Module):
             kv = ops.linear(encoder_hidden_states.reshape(B * Nk, -1), attn.fused_kv_weight())
             _, o = _cross_attention(attn, x, kv, B, N, Nk, C, ln_stats=ln_stats, ln_eps=ln_eps)
         res2d = None if residual is None else residual.reshape(B * N, C)
+        ops.prefetch_next(getattr(attn, "_next_w", None))                         # weight of the GEMM that follows this block part
         out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d,
                          stats_out=stats_out)                                     # :320 (+ fused h + ...)
         return out.reshape(B, N, C)
@@ -188,6 +191,7 @@ class IPAttnProcessor2_0(torch.nn.Module):
             qh = q.reshape(B, N, attn.heads, 64).permute(0, 2, 1, 3)
             self.attn_map = qh @ k_ip.transpose(-2, -1).softmax(dim=-1)           # :443-444 (diagnostic only)
         res2d = None if residual is None else residual.reshape(B * N, C)
+        ops.prefetch_next(getattr(attn, "_next_w", None))
         out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d, stats_out=stats_out)   # :453
         return out.reshape(B, N, C)
 

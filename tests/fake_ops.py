@@ -230,6 +230,10 @@ def workspace_generation():
     return 0
 
 
+def prefetch_next(w):
+    return None
+
+
 def euler_step(noise_pred, latents, model_in, sigmas, step, guidance, *, use_cfg=True, guidance_rescale=0.0):
     if use_cfg and not guidance_rescale:
         return euler_cfg_step(noise_pred, latents, model_in, sigmas, step, guidance)
