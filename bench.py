@@ -284,8 +284,9 @@ class FamilyTimer:
     }
 
     def __init__(self):
-        self.records = []      # (family, flops, bytes, ev0, ev1)
+        self.records = []      # (family, flops, bytes, ev0, ev1, shape label)
         self.active = False    # True only inside DenoiseEngine._step: the once-per-call K/V projections are not a step
+        self.shapes = {}       # shape label -> [calls, ms, flops]  (IH_BENCH_SHAPES=1 dumps it to gpurun_out/)
 
     def _wrap(self, ops, name, classify):
         orig = getattr(ops, name)
@@ -298,7 +299,9 @@ class FamilyTimer:
             e0.record()
             out = orig(*a, **k)
             e1.record()
-            self.records.append((fam, flops, nbytes, e0, e1))
+            label = name + ":" + "x".join(str(int(v)) for v in (list(a[0].shape) + list(a[1].shape)) if v) if name in ("linear", "conv3x3") \
+                else name + ":" + "x".join(str(v) for v in a[3:7]) if name == "attention" else name
+            self.records.append((fam, flops, nbytes, e0, e1, label))
             return out
         setattr(ops, name, wrapped)
         return orig
@@ -356,12 +359,24 @@ class FamilyTimer:
             for name, fn in saved.items():
                 setattr(ops, name, fn)
         agg = {}
-        for fam, flops, nbytes, e0, e1 in self.records:
+        for fam, flops, nbytes, e0, e1, label in self.records:
             a = agg.setdefault(fam, {"launch_groups": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            ms = e0.elapsed_time(e1)
             a["launch_groups"] += 1
-            a["ms"] += e0.elapsed_time(e1)
+            a["ms"] += ms
             a["flops"] += flops
             a["bytes"] += nbytes
+            sh = self.shapes.setdefault(fam + " " + label, [0, 0.0, 0.0])
+            sh[0] += 1
+            sh[1] += ms
+            sh[2] += flops
+        if os.environ.get("IH_BENCH_SHAPES", "0") == "1":
+            rows = sorted(self.shapes.items(), key=lambda kv: -kv[1][1])
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "bench_shapes.md"), "w") as f:
+                f.write("| family op:shape (x rows x cols | w) | calls | total ms | avg us | TFLOP/s |\n|---|---:|---:|---:|---:|\n")
+                for k, (n, ms, fl) in rows:
+                    f.write(f"| {k} | {n} | {ms:.3f} | {ms / n * 1e3:.1f} | {fl / (ms * 1e-3) / 1e12 if fl else 0:.0f} |\n")
         return agg
 
 

@@ -722,7 +722,11 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
     pair = true;
     force_bn = 256;
   } else if (force_bn == 0 && pair_mode() != 0 && (geglu || p.N >= 256)) {
-    pair = pair_mode() == 2 || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, p.num_kb);
+    static const bool geglu_pair = [] {   // IH_GEGLU_PAIR=1: always run the GEGLU GEMM on CTA-pair tiles (A/B switch)
+      const char* e = getenv("IH_GEGLU_PAIR");
+      return e && e[0] == '1';
+    }();
+    pair = pair_mode() == 2 || (geglu && geglu_pair) || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, p.num_kb);
   }
   int bn = (geglu || pair) ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
   CUtensorMap bmap;
