@@ -88,15 +88,19 @@ def test_native_processors_match_reference_goldens():
         out = proc(attn, hid.cuda(), encoder_hidden_states=ehs.cuda())
         torch.cuda.synchronize()
         assert torch.allclose(out.float().cpu(), ref, rtol=2e-3, atol=2e-3), (out.float().cpu() - ref).abs().max()
-        # and stays close to the un-rounded golden output of the real reference class
-        assert (out.float().cpu() - g["out"]).abs().max() < 2e-2
+        # and stays close to the un-rounded golden output of the real reference class (fp16 rounding of the weights included)
+        e_gold, rng = (out.float().cpu() - g["out"]).abs().max().item(), g["out"].abs().max().item()
+        print(f"[toy golden ipattn skip={skip}] max|err| {e_gold:.3e} of range {rng:.3e}")
+        assert e_gold < 5e-3 * max(rng, 1.0)
     g = gold["selfattn"]
     C = g["hidden"].shape[-1]
     attn = Attention(C, g["heads"])
     attn.load_state_dict(g["attn"])
     attn = attn.half().cuda()
     out = AttnProcessor2_0()(attn, g["hidden"].half().cuda())
-    assert (out.float().cpu() - g["out"]).abs().max() < 2e-2
+    e_gold, rng = (out.float().cpu() - g["out"]).abs().max().item(), g["out"].abs().max().item()
+    print(f"[toy golden selfattn] max|err| {e_gold:.3e} of range {rng:.3e}")
+    assert e_gold < 5e-3 * max(rng, 1.0)
 
 
 def test_unet_forward_tiny_matches_oracle():
@@ -201,10 +205,11 @@ def test_adapter_modules_match_reference_goldens_on_gpu():
     want = ref(text.float(), img.float())
     got = ha(text.cuda(), img.cuda())
     torch.cuda.synchronize()
-    assert torch.allclose(got.float().cpu(), want, rtol=5e-3, atol=5e-3), (got.float().cpu() - want).abs().max()
-    assert (got.float().cpu() - g["out"]).abs().max() < 3e-2
+    print(f"[toy golden HarmonyAttention] max|err| {(got.float().cpu() - want).abs().max().item():.3e}")
+    assert torch.allclose(got.float().cpu(), want, rtol=3e-3, atol=3e-3), (got.float().cpu() - want).abs().max()
+    assert (got.float().cpu() - g["out"]).abs().max() < 1e-2
     fused = ha(text.cuda(), img.cuda(), add_to=img.cuda())
-    assert torch.allclose(fused.float().cpu(), img.float() + want, rtol=5e-3, atol=5e-3)
+    assert torch.allclose(fused.float().cpu(), img.float() + want, rtol=3e-3, atol=3e-3)
 
     g = gold["imageproj"]
     ip = N.ImageProjModel(128, 64, 4)
@@ -213,7 +218,7 @@ def test_adapter_modules_match_reference_goldens_on_gpu():
     rip = A.ImageProjRef(128, 64, 4)
     rip.load_state_dict({k: v.half().float() for k, v in g["state"].items()})
     x = g["image"].half()
-    assert torch.allclose(ip(x.cuda()).float().cpu(), rip(x.float()), rtol=5e-3, atol=5e-3)
+    assert torch.allclose(ip(x.cuda()).float().cpu(), rip(x.float()), rtol=3e-3, atol=3e-3)
 
     g = gold["resampler"]
     r = N.Resampler(**g["kwargs"])
@@ -226,7 +231,8 @@ def test_adapter_modules_match_reference_goldens_on_gpu():
     torch.cuda.synchronize()
     want = rr(x.float())
     assert got.shape == (2, 12, 160)
-    assert torch.allclose(got.float().cpu(), want, rtol=1e-2, atol=1e-2), (got.float().cpu() - want).abs().max()
+    print(f"[toy golden Resampler] max|err| {(got.float().cpu() - want).abs().max().item():.3e} of range {want.abs().max().item():.3e}")
+    assert torch.allclose(got.float().cpu(), want, rtol=4e-3, atol=4e-3), (got.float().cpu() - want).abs().max()
 
 
 def test_ip_adapter_xl_generate_on_gpu_matches_oracle_latents():

@@ -16,5 +16,8 @@ python tools/gemm_trace.py > gpurun_out/re_gemm_trace.txt 2>&1
 python tools/sweep.py > gpurun_out/re_sweep.log 2>&1
 python tools/microbench.py > gpurun_out/re_microbench.log 2>&1
 python tools/edit_latency.py > gpurun_out/re_edit_latency.log 2>&1
+python tools/layer_head_to_head.py > gpurun_out/re_layer.log 2>&1
+IH_XATTN_FUSED=1 python tools/layer_head_to_head.py > gpurun_out/re_layer_fused.log 2>&1
+python tools/eager_ref_gpu.py 1024 1 > gpurun_out/re_eager.log 2>&1
 tail -3 gpurun_out/re_pytest.txt; tail -2 gpurun_out/re_smoke.txt; cut -c1-400 gpurun_out/re_bench_n1.json; echo; cut -c1-300 gpurun_out/re_bench_reference.json; echo
 tail -20 gpurun_out/re_sweep.log
