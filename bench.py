@@ -564,7 +564,8 @@ def run_pns(args, eng, cfg, lat, K, W, rank, world, device, dist):
         return eng.run(preview, rep(pos1, 1), rep(neg1, 1), rep(pooled1, 1), rep(npooled1, 1), rep(tid1, 1), K,
                        guidance_scale=5.0, ip_scale=1.0, start_step=P)
 
-    scorer = LinearProbeScorer(4 * lat * lat, seed=99, device=device)
+    scorer = build_clip_judge(device) if args.pns_judge == "clip" else LinearProbeScorer(4 * lat * lat, seed=99, device=device)
+    scorer(torch.zeros((1, 4, lat, lat), dtype=torch.float16, device=device))          # warm the judge
     mine = shard_seeds(seeds, rank, world)
     if mine:                                           # warm-up: capture the graphs for this rank's batch sizes
         for bsz in sorted({min(args.pns_batch, len(mine)), len(mine) % args.pns_batch or args.pns_batch} | ({1} if P else set())):

@@ -23,6 +23,12 @@ def main():
         d = jline(os.path.join(G, src))
         if d:
             json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
+    for src, dst in (("n8_bench.json", "r2_bench_n8.json"), ("n8_pns32.json", "r2_pns32_n8.json"),
+                     ("n8_pns32_two_phase.json", "r2_pns32_two_phase_n8.json"), ("c6_bench_n2.json", "r2_bench_n2.json")):
+        if os.path.exists(os.path.join(G, src)):
+            d = jline(os.path.join(G, src))
+            if d:
+                json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
     for src, dst in (("re_pytest.txt", "r2_pytest_gpu.txt"), ("re_smoke.txt", "r2_smoke.txt"), ("re_launches.md", "r2_launches_step1024.md"),
                      ("re_gemm_trace.txt", "r2_gemm_trace.txt"), ("bench_shapes.md", "r2_step_shapes.md")):
         if os.path.exists(os.path.join(G, src)):
