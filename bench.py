@@ -406,10 +406,14 @@ def family_roofline(agg, pk, step_ms_graph):
     return {"bound": d.get("bound", "tensor"), "kernel": d["kernel"], "family": dom, "achieved": d.get("achieved"),
             "peak": pk["tflops_sustained"] if d.get("bound") == "tensor" else pk["hbm_gbs"], "unit": d.get("unit"),
             "frac": d.get("frac"), "share_of_step": d["share"], "traffic": traffic, "traffic_source": tsrc,
+            "event_ms_total": total, "graph_ms_per_step": step_ms_graph,
+            "frac_if_scaled_to_graph_time": (d.get("frac") * total / step_ms_graph) if d.get("frac") else None,
             "peak_source": pk["source"] + "; sustained figure: the families are timed inside a full step",
             "how": "one eager denoise step, CUDA-event pair around every launch, queued behind a spin kernel; achieved = "
                    "family algorithmic FLOPs (bytes for GroupNorm) / family time; sum of event times "
-                   f"{total:.2f} ms vs {step_ms_graph:.2f} ms graph-replayed (events suppress PDL overlap)",
+                   f"{total:.2f} ms vs {step_ms_graph:.2f} ms graph-replayed (event pairs add idle time per launch and suppress PDL "
+                   "overlap, so `achieved` / `frac` are LOWER bounds; `frac_if_scaled_to_graph_time` spreads the graph-replayed "
+                   "step time over the families by their event-time shares)",
             "families": fams}
 
 
