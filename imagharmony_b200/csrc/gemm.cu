@@ -753,11 +753,17 @@ static unsigned long long* g_trace = nullptr;
 // one-shot hint consumed by the next GEMM / conv launch of this thread (ih_gemm_prefetch_next)
 static thread_local const void* g_pf_ptr = nullptr;
 static thread_local unsigned long long g_pf_bytes = 0;
-static void take_prefetch_hint(GemmParams& p) {
-  p.pf_ptr = (const unsigned char*)g_pf_ptr;
-  p.pf_bytes = g_pf_bytes;
+// The hint is consumed by the FIRST launch attempt after it was set, whether or not that call gets as far as launching:
+// a call that fails validation must not leave a pointer behind for an unrelated later launch.
+struct PrefetchHint {
+  const unsigned char* ptr;
+  unsigned long long bytes;
+};
+static PrefetchHint take_prefetch_hint() {
+  PrefetchHint h{(const unsigned char*)g_pf_ptr, g_pf_bytes};
   g_pf_ptr = nullptr;
   g_pf_bytes = 0;
+  return h;
 }
 }  // namespace ih
 
@@ -804,6 +810,7 @@ static int gemm_impl(const void* a, long long lda, const void* w, const void* bi
                      int rows_per_group, long long ld_rowbias, const void* residual, long long ldr, void* out,
                      long long ldo, int M, int N, int K, int epilogue, int tile_n, const void* ln_stats,
                      int ln_slabs, float ln_eps, void* stats_out, float alpha, void* stream) {
+  const PrefetchHint hint = take_prefetch_hint();
   IH_CHECK(a && w && out, IH_ERR_ARG, "ih_gemm_f16: null pointer");
   IH_CHECK(M > 0 && N > 0 && K > 0, IH_ERR_SHAPE, "ih_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
   IH_CHECK(K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, IH_ERR_ALIGN,
@@ -838,7 +845,8 @@ static int gemm_impl(const void* a, long long lda, const void* w, const void* bi
   p.ldo = ldo;
   p.act = (epilogue & IH_EPI_SILU) ? 1 : ((epilogue & IH_EPI_GELU) ? 2 : ((epilogue & IH_EPI_QUICK_GELU) ? 3 : 0));
   p.trace = g_trace;
-  take_prefetch_hint(p);
+  p.pf_ptr = hint.ptr;
+  p.pf_bytes = hint.bytes;
   IH_CHECK(!ln_stats || ln_slabs > 0, IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_slabs > 0");
   IH_CHECK(!stats_out || N % 64 == 0 || geglu, IH_ERR_SHAPE, "ih_gemm_ln_f16: stats_out needs N %% 64 == 0");
   p.stats_out = (float*)stats_out;
@@ -884,6 +892,7 @@ extern "C" int ih_conv2d_scaled_f16(const void* x, const void* w, const void* bi
 static int conv_impl(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
                      const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
                      int tile_n, float alpha, void* stream) {
+  const PrefetchHint hint = take_prefetch_hint();
   IH_CHECK(x && w && out, IH_ERR_ARG, "ih_conv2d_f16: null pointer");
   IH_CHECK(ksize == 3, IH_ERR_ARG, "ih_conv2d_f16: ksize must be 3 (1x1 convs are ih_gemm_f16)");
   IH_CHECK(stride == 1 || stride == 2, IH_ERR_ARG, "ih_conv2d_f16: stride must be 1 or 2");
@@ -923,7 +932,8 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
   p.out = (__half*)out;
   p.ldo = Cout;
   p.trace = g_trace;
-  take_prefetch_hint(p);
+  p.pf_ptr = hint.ptr;
+  p.pf_bytes = hint.bytes;
   p.alpha = alpha;
 
   TmapSet4 amaps;
