@@ -319,7 +319,8 @@ class FamilyTimer:
             s = k.get("stride", 1)
             Cout = w.shape[0]
             px = B * (H // s) * (W // s)
-            return "conv3x3", 18.0 * Cin * Cout * px, 2.0 * (B * H * W * Cin + px * Cout + 9 * Cin * Cout)
+            csc = w.shape[1] - 9 * Cin                  # fused 1x1 shortcut columns (ResBlock conv2)
+            return "conv3x3", (18.0 * Cin + 2.0 * csc) * Cout * px, 2.0 * (B * H * W * (Cin + csc) + px * Cout + w.shape[1] * Cout)
 
         def c_attn(q, k_, v, B, H, Nq, Nk, **k):
             return ("attn_self" if Nk > 128 else "attn_cross"), 4.0 * B * H * Nq * Nk * 64, 2.0 * 64 * B * H * (2 * Nq + 2 * Nk)

@@ -70,6 +70,8 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ih_conv2d_scaled_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p]),
+    "ih_conv2d_shortcut_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_int,
+                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ih_gemm_set_trace": (None, [c_void_p]),
     "ih_gemm_prefetch_next": (None, [c_void_p, c_longlong]),
     "ih_conv2d_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,

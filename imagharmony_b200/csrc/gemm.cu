@@ -39,7 +39,13 @@ struct GemmParams {
   int m_tiles;  // number of 128-row output tiles
   int num_kb;   // K blocks of 64 (taps * cin_kb for conv)
   int mode;     // 0 = plain GEMM, 1 = conv (4-D A maps)
-  int cin_kb;   // conv: K blocks per tap
+  int cin_kb;   // conv: K blocks per 3x3 tap
+  // conv: cumulative K-block end of every tap.  Taps 0..8 are the 3x3 window; taps 9 / 10 (optional) are a fused 1x1
+  // SHORTCUT convolution over one or two further NHWC sources (ResnetBlock2D conv_shortcut on the channel concat of the
+  // hidden state and the skip connection): their K blocks accumulate into the same TMEM tile, so `conv2(h) + shortcut(
+  // cat(x, skip))` is ONE launch and the concatenated tensor is never materialised.
+  int n_taps;
+  int tap_kb_end[12];
   int Ho, Wo;   // conv: output spatial size
   int bw, bh;   // conv: spatial tile (bw*bh == 128)
   int tiles_x, tiles_y;
@@ -203,8 +209,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
             if (p.mode == 0) {
               tma_load_2d_2sm(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
             } else {
-              const int tap = kb / p.cin_kb;
-              const int ckb = kb - tap * p.cin_kb;
+              int tap = 0;
+              while (kb >= p.tap_kb_end[tap]) ++tap;
+              const int ckb = kb - (tap ? p.tap_kb_end[tap - 1] : 0);
               tma_load_4d_2sm(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
                               y0 + p.tap_oy[tap], img);
             }
@@ -216,8 +223,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
             if (p.mode == 0) {
               tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
             } else {
-              const int tap = kb / p.cin_kb;
-              const int ckb = kb - tap * p.cin_kb;
+              int tap = 0;
+              while (kb >= p.tap_kb_end[tap]) ++tap;
+              const int ckb = kb - (tap ? p.tap_kb_end[tap - 1] : 0);
               tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
                           y0 + p.tap_oy[tap], img);
             }
@@ -875,7 +883,8 @@ static int gemm_impl(const void* a, long long lda, const void* w, const void* bi
 
 static int conv_impl(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
                      const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
-                     int tile_n, float alpha, void* stream);
+                     int tile_n, float alpha, void* stream, const void* sc0 = nullptr, int Csc0 = 0,
+                     const void* sc1 = nullptr, int Csc1 = 0);
 
 extern "C" int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias,
                              long long ld_rowbias, const void* residual, void* out, int B, int Hin, int Win, int Cin,
@@ -889,9 +898,18 @@ extern "C" int ih_conv2d_scaled_f16(const void* x, const void* w, const void* bi
   return conv_impl(x, w, bias, nullptr, 0, residual, out, B, Hin, Win, Cin, Cout, 3, stride, 0, alpha, stream);
 }
 
+extern "C" int ih_conv2d_shortcut_f16(const void* x, const void* w, const void* bias, const void* rowbias,
+                                      long long ld_rowbias, const void* sc0, int Csc0, const void* sc1, int Csc1, void* out,
+                                      int B, int H, int W, int Cin, int Cout, void* stream) {
+  IH_CHECK(sc0 && Csc0 > 0 && Csc0 % BK == 0 && (!sc1 || (Csc1 > 0 && Csc1 % BK == 0)), IH_ERR_SHAPE,
+           "ih_conv2d_shortcut_f16: shortcut sources need channel counts that are multiples of 64");
+  return conv_impl(x, w, bias, rowbias, ld_rowbias, nullptr, out, B, H, W, Cin, Cout, 3, 1, 0, 1.f, stream, sc0, Csc0,
+                   sc1 ? sc1 : nullptr, sc1 ? Csc1 : 0);
+}
+
 static int conv_impl(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
                      const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
-                     int tile_n, float alpha, void* stream) {
+                     int tile_n, float alpha, void* stream, const void* sc0, int Csc0, const void* sc1, int Csc1) {
   const PrefetchHint hint = take_prefetch_hint();
   IH_CHECK(x && w && out, IH_ERR_ARG, "ih_conv2d_f16: null pointer");
   IH_CHECK(ksize == 3, IH_ERR_ARG, "ih_conv2d_f16: ksize must be 3 (1x1 convs are ih_gemm_f16)");
@@ -920,7 +938,18 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
   p.Wo = Wo;
   p.mode = 1;
   p.cin_kb = (Cin + BK - 1) / BK;
-  p.num_kb = 9 * p.cin_kb;
+  p.n_taps = 9;
+  for (int t = 0; t < 9; ++t) p.tap_kb_end[t] = (t + 1) * p.cin_kb;
+  if (sc0) {
+    p.tap_kb_end[9] = p.tap_kb_end[8] + Csc0 / BK;
+    p.n_taps = 10;
+    if (sc1) {
+      p.tap_kb_end[10] = p.tap_kb_end[9] + Csc1 / BK;
+      p.n_taps = 11;
+    }
+  }
+  for (int t = p.n_taps; t < 12; ++t) p.tap_kb_end[t] = 0x7fffffff;   // sentinel: the tap search always terminates
+  p.num_kb = p.tap_kb_end[p.n_taps - 1];
   p.M = B * Ho * Wo;
   p.N = Cout;
   p.bias = (const __half*)bias;
@@ -949,7 +978,18 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
       p.tap_ox[t] = (signed char)(t % 3 - 1);
       p.tap_oy[t] = (signed char)(t / 3 - 1);
     }
+    const void* srcs[2] = {sc0, sc1};
+    const int chans[2] = {Csc0, Csc1};
+    for (int i = 0; i < 2 && srcs[i]; ++i) {       // fused 1x1 shortcut sources: centre tap of their own tensor maps
+      const uint64_t sdims[4] = {(uint64_t)chans[i], (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+      const uint64_t sstr[3] = {(uint64_t)chans[i] * 2, (uint64_t)Win * chans[i] * 2, (uint64_t)Hin * Win * chans[i] * 2};
+      rc = get_tmap_f16(&amaps.m[1 + i], srcs[i], 4, sdims, sstr, abox);
+      if (rc) return rc;
+      p.tap_map[9 + i] = (signed char)(1 + i);
+      p.tap_ox[9 + i] = p.tap_oy[9 + i] = 0;
+    }
   } else {
+    IH_CHECK(!sc0, IH_ERR_ARG, "ih_conv2d: a fused shortcut needs stride 1");
     // input row 2*oy + dy - 1: dy=0 -> odd rows at oy-1, dy=1 -> even rows at oy, dy=2 -> odd rows at oy
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
@@ -984,5 +1024,5 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
       if (rc) return rc;
     }
   }
-  return dispatch(amaps, omap, rmap, w, Cout, (long long)9 * Cin, p, m_tiles, 0, tile_n, (cudaStream_t)stream);
+  return dispatch(amaps, omap, rmap, w, Cout, (long long)9 * Cin + Csc0 + Csc1, p, m_tiles, 0, tile_n, (cudaStream_t)stream);
 }

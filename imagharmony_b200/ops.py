@@ -128,12 +128,33 @@ def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.T
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
             rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, stride: int = 1,
-            out: Optional[torch.Tensor] = None, tile_n: int = 0, alpha: float = 1.0) -> torch.Tensor:
-    """3x3 conv, pad 1. x NHWC [B,H,W,Cin]; w_packed [Cout, 9*Cin] (see pack_conv3x3_weight); rowbias [B, >=Cout]."""
+            out: Optional[torch.Tensor] = None, tile_n: int = 0, alpha: float = 1.0, shortcut=None) -> torch.Tensor:
+    """3x3 conv, pad 1. x NHWC [B,H,W,Cin]; w_packed [Cout, 9*Cin] (see pack_conv3x3_weight); rowbias [B, >=Cout].
+    `shortcut=(s0, s1 | None)`: fused 1x1 shortcut conv over the channel concat of the NHWC tensors s0 [, s1]; then
+    w_packed is [Cout, 9*Cin + C(s0) + C(s1)] (3x3 taps followed by the shortcut weight), see ih_conv2d_shortcut_f16."""
     lib = _lib.load()
     _req(x, "x"); _req(w_packed, "w")
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
+    if shortcut is not None:
+        s0, s1 = shortcut
+        c0, c1 = s0.shape[-1], (0 if s1 is None else s1.shape[-1])
+        _req(s0, "shortcut[0]")
+        if s1 is not None:
+            _req(s1, "shortcut[1]")
+        if (stride != 1 or residual is not None or alpha != 1.0 or tile_n or not x.is_contiguous() or not s0.is_contiguous()
+                or (s1 is not None and not s1.is_contiguous()) or tuple(s0.shape[:3]) != (B, H, W)
+                or (s1 is not None and tuple(s1.shape[:3]) != (B, H, W)) or not w_packed.is_contiguous()
+                or w_packed.shape[1] != 9 * Cin + c0 + c1):
+            raise IHError("conv3x3(shortcut=): stride 1, no residual / alpha / tile_n, contiguous NHWC sources of the same "
+                          "spatial size and w_packed [Cout, 9*Cin + C0 + C1] required")
+        if out is None:
+            out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x.device)
+        ldrb = _rows(rowbias, "rowbias") if rowbias is not None else 0
+        rc = lib.ih_conv2d_shortcut_f16(x.data_ptr(), w_packed.data_ptr(), _p(bias), _p(rowbias), ldrb, s0.data_ptr(), c0,
+                                        _p(s1), c1, out.data_ptr(), B, H, W, Cin, Cout, _stream())
+        check(rc, "ih_conv2d_shortcut_f16")
+        return out
     if not x.is_contiguous() or not w_packed.is_contiguous() or w_packed.shape[1] != 9 * Cin:
         raise IHError("conv3x3: x must be contiguous NHWC and w_packed [Cout, 9*Cin]")
     Ho, Wo = H // stride, W // stride

@@ -101,6 +101,9 @@ class ResnetBlock2D(nn.Module):
         self._w2 = ops.pack_conv3x3_weight(self.conv2.weight.detach())
         if self.conv_shortcut is not None:
             self._wsc = self.conv_shortcut.weight.detach().reshape(self.cout, self.cin).contiguous()
+            # conv2 with the 1x1 shortcut (and the skip concat of the up-blocks) as extra K blocks of the same launch
+            self._w2sc = torch.cat([self._w2, self._wsc], dim=1).contiguous()
+            self._b2sc = (self.conv2.bias.detach().float() + self.conv_shortcut.bias.detach().float()).to(self._w2.dtype)
 
     def forward(self, x: torch.Tensor, temb_all: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x NHWC [B,H,W,C0] (+ skip [B,H,W,C1] concatenated on channels); temb_all [B, sum(Cout)]."""
@@ -111,6 +114,9 @@ class ResnetBlock2D(nn.Module):
         h = ops.conv3x3(h, self._w1, self.conv1.bias, rowbias=temb)
         h = ops.groupnorm(h, self.norm2.weight, self.norm2.bias, groups=self.groups, eps=1e-5, silu=True)
         if self.conv_shortcut is not None:
+            c0, c1 = x.shape[-1], (0 if skip is None else skip.shape[-1])
+            if c0 % 64 == 0 and c1 % 64 == 0:      # every SDXL ResBlock: shortcut + concat fused into conv2
+                return ops.conv3x3(h, self._w2sc, self._b2sc, shortcut=(x, skip))
             xin = x if skip is None else ops.concat_channels(x, skip)
             sc = ops.linear(xin.reshape(B * H * W, self.cin), self._wsc, self.conv_shortcut.bias)
             sc = sc.reshape(B, H, W, self.cout)

@@ -77,6 +77,14 @@ void ih_gemm_set_trace(void* device_buffer);
 int ih_conv2d_f16(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
                   const void* residual, void* out, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
                   int tile_n, void* stream);
+/* 3x3 conv (stride 1, pad 1) with a FUSED 1x1 shortcut convolution over one or two further NHWC sources:
+ *   out = conv3x3(x) + [sc0 | sc1] Wsc^T + bias + rowbias        w = [Cout, 9*Cin + Csc0 + Csc1] (3x3 taps, then Wsc)
+ * i.e. diffusers ResnetBlock2D `conv2(h) + conv_shortcut(cat(hidden, skip))` as ONE launch: the shortcut's K blocks
+ * accumulate into the same TMEM tile and the channel concat of the up-blocks is never materialised.  Csc0, Csc1 % 64 == 0;
+ * sc1 may be NULL. */
+int ih_conv2d_shortcut_f16(const void* x, const void* w, const void* bias, const void* rowbias, long long ld_rowbias,
+                           const void* sc0, int Csc0, const void* sc1, int Csc1, void* out, int B, int H, int W, int Cin,
+                           int Cout, void* stream);
 /* out = alpha * conv(x) + bias + residual (3x3, pad 1): the VAE decoder's scaled residual stream, see ih_gemm_scaled_f16. */
 int ih_conv2d_scaled_f16(const void* x, const void* w, const void* bias, const void* residual, void* out, int B, int Hin,
                          int Win, int Cin, int Cout, int stride, float alpha, void* stream);

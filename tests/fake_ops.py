@@ -107,10 +107,15 @@ def pack_conv3x3_weight(w):
     return w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
 
 
-def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, out=None, tile_n=0, alpha=1.0):
+def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, out=None, tile_n=0, alpha=1.0, shortcut=None):
     _count[0] += 1
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
+    sc_term = None
+    if shortcut is not None:
+        src = shortcut[0] if shortcut[1] is None else torch.cat([shortcut[0], shortcut[1]], dim=-1)
+        sc_term = src.float() @ w_packed[:, 9 * Cin:].float().t()
+        w_packed = w_packed[:, : 9 * Cin]
     w = w_packed.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).float()
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride=stride, padding=1).permute(0, 2, 3, 1) * alpha
     if bias is not None:
@@ -119,6 +124,8 @@ def conv3x3(x, w_packed, bias=None, *, rowbias=None, residual=None, stride=1, ou
         y = y + rowbias.float()[:, None, None, :]
     if residual is not None:
         y = y + residual.float()
+    if sc_term is not None:
+        y = y + sc_term
     return y.to(x.dtype).contiguous()
 
 

@@ -485,3 +485,23 @@ def test_euler_step_ex(ops, use_cfg, rescale):
     m2 = torch.empty_like(model_in)
     ops.scale_model_input(lat, m2, sig, step, duplicate=use_cfg)
     check(m2, torch.cat([mi, mi]) if use_cfg else mi, "scale_model_input_ex")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,C0,C1", [(2, 32, 32, 128, 192, 64, 0), (2, 16, 16, 256, 128, 192, 64),
+                                                   (1, 24, 40, 64, 320, 128, 192), (2, 32, 32, 1280, 1280, 1280, 1280)])
+def test_conv3x3_fused_shortcut(ops, B, H, W, Cin, Cout, C0, C1):
+    """conv2(h) + conv_shortcut(cat(x, skip)) of a ResnetBlock2D as ONE implicit-GEMM launch (extra K blocks over one or two
+    further NHWC sources) against conv2d + 1x1 conv in fp32."""
+    h = rnd(B, H, W, Cin, seed=1)
+    w3 = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    x0 = rnd(B, H, W, C0, seed=3)
+    x1 = rnd(B, H, W, C1, seed=4) if C1 else None
+    wsc = rnd(Cout, C0 + C1, scale=(C0 + C1) ** -0.5, seed=5)
+    bias = rnd(Cout, seed=6)
+    temb = rnd(B, Cout, seed=7)
+    w_ext = torch.cat([ops.pack_conv3x3_weight(w3), wsc], dim=1).contiguous()
+    out = ops.conv3x3(h, w_ext, bias, rowbias=temb, shortcut=(x0, x1))
+    src = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    ref = (F.conv2d(h.float().permute(0, 3, 1, 2), w3.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+           + src.float() @ wsc.float().t() + temb.float()[:, None, None, :])
+    check(out, ref, f"conv3x3 + fused shortcut {Cin}->{Cout} sc {C0}+{C1}")
