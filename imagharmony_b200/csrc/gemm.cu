@@ -197,7 +197,14 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
           y0 = (t / p.tiles_x) * p.bh;
           x0 = (t % p.tiles_x) * p.bw;
         }
+        // conv: the tap of a K block is tracked incrementally (warp-uniform registers): tap_lo <= kb < tap_hi
+        int tap = 0, tap_lo = 0, tap_hi = p.mode == 1 ? p.tap_kb_end[0] : 0x7fffffff;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (kb == tap_hi) {
+            ++tap;
+            tap_lo = tap_hi;
+            tap_hi = p.tap_kb_end[tap];
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * S::STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
@@ -209,9 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
             if (p.mode == 0) {
               tma_load_2d_2sm(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
             } else {
-              int tap = 0;
-              while (kb >= p.tap_kb_end[tap]) ++tap;
-              const int ckb = kb - (tap ? p.tap_kb_end[tap - 1] : 0);
+              const int ckb = kb - tap_lo;
               tma_load_4d_2sm(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
                               y0 + p.tap_oy[tap], img);
             }
@@ -223,9 +228,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
             if (p.mode == 0) {
               tma_load_2d(sA, &amaps.m[0], &full_bar[stage], kb * BK, m0);
             } else {
-              int tap = 0;
-              while (kb >= p.tap_kb_end[tap]) ++tap;
-              const int ckb = kb - (tap ? p.tap_kb_end[tap - 1] : 0);
+              const int ckb = kb - tap_lo;
               tma_load_4d(sA, &amaps.m[p.tap_map[tap]], &full_bar[stage], ckb * BK, x0 + p.tap_ox[tap],
                           y0 + p.tap_oy[tap], img);
             }
