@@ -727,8 +727,20 @@ static bool pair_is_faster(long long m_tiles, int n_cols, int num_kb) {
 
 static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtensorMap& rmap, const void* w, int ldw_rows,
                     long long K, GemmParams& p, int m_tiles, int geglu, int force_bn, cudaStream_t stream) {
-  // tile_n = 512 forces the CTA-pair 256x256 tile, other explicit values force the single-CTA tile of that width
+  // tile_n = 512 forces the CTA-pair 256x256 tile, 384 the CTA-pair 256x192 tile, other explicit values force the
+  // single-CTA tile of that width
   bool pair = false;
+  if (force_bn == 384 && !geglu) {
+    // CTA-pair 256x192: the same tile count per SM as the single-CTA 128x192 tile, but every SM streams half of B
+    // (28 instead of 40 KB per k-block)
+    CUtensorMap bmap192;
+    const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)ldw_rows};
+    const uint64_t bstr[1] = {(uint64_t)K * 2};
+    const uint32_t bbox[2] = {(uint32_t)BK, 96u};
+    int rc = get_tmap_f16(&bmap192, w, 2, bdims, bstr, bbox);
+    if (rc) return rc;
+    return launch_gemm<192, 6, false, true>(amaps, bmap192, omap, rmap, p, m_tiles, stream);
+  }
   if (force_bn == 512) {
     pair = true;
     force_bn = 256;
