@@ -730,9 +730,19 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
   // tile_n = 512 forces the CTA-pair 256x256 tile, 384 the CTA-pair 256x192 tile, other explicit values force the
   // single-CTA tile of that width
   bool pair = false;
-  if (force_bn == 384 && !geglu) {
-    // CTA-pair 256x192: the same tile count per SM as the single-CTA 128x192 tile, but every SM streams half of B
-    // (28 instead of 40 KB per k-block)
+  // CTA-pair 256x192 tile: the same tiles per SM as the single-CTA 128x192 tile, but every SM streams half of B (28
+  // instead of 40 KB per k-block).  The main loop is bound by the L2 -> SM operand stream, so long-K launches gain
+  // (tools/tile_probe.py, profiles/r2_tile_probe.txt: conv3x3 2560->1280 118 -> 95 us, 1280->1280 53 -> 50 us, FF-out
+  // K = 5120 27.5 -> 26.2 us) while the ~0.5 us of cluster set-up loses on K = 1280 (11.1 -> 11.5 us): used from 40
+  // k-blocks on.  IH_PAIR192=0 disables the heuristic.
+  static const bool pair192_on = [] {
+    const char* e = getenv("IH_PAIR192");
+    return !(e && e[0] == '0');
+  }();
+  const bool want_pair192 = force_bn == 384 || (force_bn == 0 && pair192_on && !geglu && p.num_kb >= 40 && m_tiles >= 2 &&
+                                                 p.N > 64 && pick_bn(m_tiles, p.N) == 192 &&
+                                                 !(pair_mode() != 0 && p.N >= 256 && pair_is_faster(m_tiles, p.N, p.num_kb)));
+  if (want_pair192 && !geglu) {
     CUtensorMap bmap192;
     const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)ldw_rows};
     const uint64_t bstr[1] = {(uint64_t)K * 2};

@@ -59,6 +59,10 @@ def check(out, ref, what, rtol=RTOL, atol=ATOL):
     (1000, 1920, 640, 512),
     (2048, 1280, 1280, 192),  # 128x192 tiles: 7 N tiles, the last one clipped at N
     (300, 200, 320, 192),
+    (2048, 1280, 5120, 384),  # CTA-pair 256x192 tile (long K: the shape it is chosen for)
+    (384, 1280, 640, 384),    # CTA-pair 256x192, odd number of 128-row tiles (dead half tile), clipped last N tile
+    (1000, 200, 320, 384),
+    (2048, 1280, 5120, 0),    # library's choice for long K
 ])
 def test_gemm_plain(ops, M, N, K, tile_n):
     x = rnd(M, K)
@@ -173,7 +177,7 @@ def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
     (2, 32, 32, 1280, 1280, 1), (2, 64, 64, 640, 640, 1), (1, 24, 24, 128, 320, 1), (2, 64, 64, 320, 320, 2),
 ])
-@pytest.mark.parametrize("tile_n", [512, 192])
+@pytest.mark.parametrize("tile_n", [512, 192, 384])
 def test_conv3x3_tile_variants(ops, B, H, W, Cin, Cout, stride, tile_n):
     x_nchw = rnd(B, Cin, H, W)
     w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
