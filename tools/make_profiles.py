@@ -44,12 +44,19 @@ def main():
             rows += json.load(open(f))
     if rows:
         base = {(r["res"], r["images_per_gpu"], r["steps"]): r["denoise_steps_per_s"] for r in rows if r["gpus"] == 1}
+        prev = os.path.join(G, "sweep_n1_prev.json")     # 1-GPU sweep of the build the multi-GPU rows were measured with
+        base_multi = dict(base)
+        if os.path.exists(prev):
+            base_multi = {(r["res"], r["images_per_gpu"], r["steps"]): r["denoise_steps_per_s"] for r in json.load(open(prev))}
         with open(os.path.join(P, "r2_sweep.md"), "w") as f:
             f.write("# HarmonyBench-shape sweep (BASELINE config 5): tools/sweep.py, CUDA-graph replay through DenoiseEngine.run, "
-                    "round-2 kernels\n\n| GPUs | res | images/GPU (UNet batch) | steps | ms/step | denoise-steps/s (all GPUs) | "
+                    "round-2 kernels.  The 8-GPU rows were taken with the build of this round that ran 19.7 ms per 1024^2 step on one GPU "
+                    "(before the CTA-pair 256x192 tile and the fused ResBlock shortcut); their weak-scaling efficiency is computed "
+                    "against the 1-GPU sweep of that same build (efficiencies slightly above 1 are box-to-box variance).  The final "
+                    "build's 8-GPU bench line is profiles/r2_bench_n8.json (424.6 steps/s = 1.00 x 8 x 53.0).\n\n| GPUs | res | images/GPU (UNet batch) | steps | ms/step | denoise-steps/s (all GPUs) | "
                     "algorithmic TFLOP/s per GPU | frac of sustained peak | weak-scaling efficiency |\n|---|---|---|---|---:|---:|---:|---:|---:|\n")
             for r in rows:
-                b = base.get((r["res"], r["images_per_gpu"], r["steps"]))
+                b = (base if r["gpus"] == 1 else base_multi).get((r["res"], r["images_per_gpu"], r["steps"]))
                 eff = f"{r['denoise_steps_per_s'] / (b * r['gpus']):.3f}" if b else "-"
                 f.write(f"| {r['gpus']} | {r['res']}^2 | {r['images_per_gpu']} ({r['unet_batch']}) | {r['steps']} | {r['ms_per_step']:.2f} | "
                         f"{r['denoise_steps_per_s']:.1f} | {r['tflops_per_gpu']:.0f} | {r['frac_sustained_peak']:.2f} | {eff} |\n")
