@@ -66,6 +66,7 @@ struct GemmParams {
   // epilogue warp issues cp.async.bulk.prefetch.L2 for this CTA's slice while the main loop runs.
   const unsigned char* pf_ptr;
   unsigned long long pf_bytes;
+  int per_slab_store;   // epilogue: TMA-store every slab right after its own barrier instead of one burst per tile
   // LayerNorm folding (plain GEMM mode only).  A producer GEMM writes, per output row and 64-column slab, the sum and
   // the sum of squares of the fp16-rounded values it stores (stats_out [ceil(N/64), M, 2] fp32, one writer per slot:
   // deterministic, nothing to zero).  The consumer GEMM multiplies the RAW rows with gamma-scaled, row-CENTRED weights
@@ -424,7 +425,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) gemm_f16_kernel(const __gri
         for (int sl = 0; sl < SLABS; ++sl)
           if (n0 + sl * 64 < p.N) last_slab = sl;
       bool arrived = false;
-      constexpr bool kOneBarrier = (NBUF == SLABS);
+      // one proxy fence + barrier + store burst per tile (every slab has its own staging buffer), or store each slab as soon
+      // as it is complete (p.per_slab_store: the earlier stores read their buffers out behind the later slabs' arithmetic)
+      const bool kOneBarrier = (NBUF == SLABS) && !p.per_slab_store;
       // after the slab is complete in shared memory (barrier): the issuer stores it; one half-group computes the row
       // statistics of exactly the fp16 values a later LayerNorm would read -- the whole 64-column row of the slab (both
       // column halves), re-read from the staging buffer; one writer per (slab, row) slot
@@ -782,6 +785,14 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
   }
 }
 
+// IH_EPI_PER_SLAB=1: per-slab TMA stores in the epilogue (A/B switch; default: one store burst per tile)
+static int per_slab_store_mode() {
+  static int m = [] {
+    const char* e = getenv("IH_EPI_PER_SLAB");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return m;
+}
 static unsigned long long* g_trace = nullptr;
 // one-shot hint consumed by the next GEMM / conv launch of this thread (ih_gemm_prefetch_next)
 static thread_local const void* g_pf_ptr = nullptr;
@@ -880,6 +891,7 @@ static int gemm_impl(const void* a, long long lda, const void* w, const void* bi
   p.trace = g_trace;
   p.pf_ptr = hint.ptr;
   p.pf_bytes = hint.bytes;
+  p.per_slab_store = per_slab_store_mode();
   IH_CHECK(!ln_stats || ln_slabs > 0, IH_ERR_ARG, "ih_gemm_ln_f16: ln_stats needs ln_slabs > 0");
   IH_CHECK(!stats_out || N % 64 == 0 || geglu, IH_ERR_SHAPE, "ih_gemm_ln_f16: stats_out needs N %% 64 == 0");
   p.stats_out = (float*)stats_out;
@@ -988,6 +1000,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, const void*
   p.trace = g_trace;
   p.pf_ptr = hint.ptr;
   p.pf_bytes = hint.bytes;
+  p.per_slab_store = per_slab_store_mode();
   p.alpha = alpha;
 
   TmapSet4 amaps;
