@@ -758,11 +758,15 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
     pair = true;
     force_bn = 256;
   } else if (force_bn == 0 && pair_mode() != 0 && (geglu || p.N >= 256)) {
-    static const bool geglu_pair = [] {   // IH_GEGLU_PAIR=1: always run the GEGLU GEMM on CTA-pair tiles (A/B switch)
+    // GEGLU on CTA-pair tiles from 20 k-blocks on: measured in the step (tools/ab_env.sh, two repeats on one box) 19.23 ->
+    // 19.10 ms for the 2048 x 10240 x 1280 FF GEGLU-in (micro-benchmark 44.3 -> 41.4 us), while the K = 640 level loses
+    // (52.3 -> 59.0 us).  IH_GEGLU_PAIR=0 / 1 overrides (never / always).
+    static const int geglu_pair = [] {
       const char* e = getenv("IH_GEGLU_PAIR");
-      return e && e[0] == '1';
+      return e ? (e[0] == '1' ? 1 : 0) : -1;
     }();
-    pair = pair_mode() == 2 || (geglu && geglu_pair) || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, p.num_kb);
+    const bool geglu_wants_pair = geglu && (geglu_pair == 1 || (geglu_pair == -1 && p.num_kb >= 20));
+    pair = pair_mode() == 2 || geglu_wants_pair || pair_is_faster(m_tiles, geglu ? 2 * p.N : p.N, p.num_kb);
   }
   int bn = (geglu || pair) ? 256 : (force_bn > 0 ? force_bn : pick_bn(m_tiles, p.N));
   CUtensorMap bmap;
