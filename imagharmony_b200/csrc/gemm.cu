@@ -742,7 +742,11 @@ static int dispatch(const TmapSet4& amaps, const CUtensorMap& omap, const CUtens
     const char* e = getenv("IH_PAIR192");
     return !(e && e[0] == '0');
   }();
-  const bool want_pair192 = force_bn == 384 || (force_bn == 0 && pair192_on && !geglu && p.num_kb >= 40 && m_tiles >= 2 &&
+  static const int pair192_min_kb = [] {
+    const char* e = getenv("IH_PAIR192_MINKB");
+    return e ? atoi(e) : 40;
+  }();
+  const bool want_pair192 = force_bn == 384 || (force_bn == 0 && pair192_on && !geglu && p.num_kb >= pair192_min_kb && m_tiles >= 2 &&
                                                  p.N > 64 && pick_bn(m_tiles, p.N) == 192 &&
                                                  !(pair_mode() != 0 && p.N >= 256 && pair_is_faster(m_tiles, p.N, p.num_kb)));
   if (want_pair192 && !geglu) {

@@ -3,7 +3,7 @@
 set -u
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-baseline --no-families"
 for rep in 1 2; do
-  for cfg in "BASE=1" "IH_EPI_PER_SLAB=1" "IH_GEGLU_PAIR=1" "IH_GN_BLOCKS_PER_SM=1" "IH_GN_BLOCKS_PER_SM=4" "IH_PAIR192=0"; do
+  for cfg in ${AB_CONFIGS:-"BASE=1" "IH_GEGLU_PAIR=0" "IH_PAIR192_MINKB=20" "IH_PAIR192_MINKB=30"}; do
     v=$(env $cfg $B 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3))")
     echo "rep $rep $cfg ms_per_step $v"
   done
