@@ -1,5 +1,6 @@
 #!/bin/bash
 set -u
-python -m pytest tests/test_kernels_gpu.py -q 2>&1 | tail -2
-python -m pytest tests/test_unet_gpu.py -q -s -k "1024" 2>&1 | grep -E "^\[unet SDXL|passed|failed|FAILED" | tail -6
-bash tools/ab_env.sh
+for v in 1 2 3; do
+  echo "variant $v: $(IH_ATTN_VARIANT=$v python -m pytest tests/test_kernels_gpu.py -q -k 'attention or attn' 2>&1 | tail -1)"
+done
+AB_CONFIGS='BASE=1 IH_ATTN_VARIANT=1 IH_ATTN_VARIANT=2 IH_ATTN_VARIANT=3' bash tools/ab_env.sh
