@@ -689,6 +689,14 @@ static int pick_bn(long long m_tiles, int N) {
   const int sms = num_sms();
   double best = 1e30;
   int best_bn = 256;
+  // 128x64 tiles for launches that cannot fill the SMs with wider ones (the 1280-channel level of a 512^2 edit has
+  // M = 512: 28 tiles of 128x192): each SM then streams 24 instead of 32-40 KB per k-block and drains one slab.
+  // Same-box A/B: 512^2 step 10.47 -> 9.84 ms (GEMMs) -> 9.76 ms (+ convs), 1024^2 unchanged.  IH_BN64=0 disables.
+  static const int bn64 = [] {
+    const char* e = getenv("IH_BN64");
+    return e ? atoi(e) : 1;
+  }();
+  if (bn64 && m_tiles * ((N + 63) / 64) <= sms) return 64;
   // per-tile main-loop cost relative to the 128x256 tile.  Measured per 64-deep k-block with 144 CTAs busy
   // (tools/ab_probe.py tile): 0.350 us (256), 0.276 us (192), 0.257 us (128) -- the narrow tiles move more operand
   // bytes per FLOP and the main loop is bound by the L2 -> SM operand stream (~19 TB/s aggregate), not by the MMA.

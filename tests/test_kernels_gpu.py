@@ -63,6 +63,8 @@ def check(out, ref, what, rtol=RTOL, atol=ATOL):
     (384, 1280, 640, 384),    # CTA-pair 256x192, odd number of 128-row tiles (dead half tile), clipped last N tile
     (1000, 200, 320, 384),
     (2048, 1280, 5120, 0),    # library's choice for long K
+    (512, 1280, 1280, 64),    # 128x64 tiles: the 1280-channel level of a 512^2 edit (80 tiles instead of 28)
+    (512, 1280, 5120, 64),
 ])
 def test_gemm_plain(ops, M, N, K, tile_n):
     x = rnd(M, K)
@@ -110,6 +112,7 @@ def test_gemm_geglu(ops, M, C, tile_n):
     (8192, 640, 640, False, 0),       # norm2 -> to_q at the 640-channel level
     (2048, 5120, 1280, True, 0),      # norm3 -> GEGLU projection
     (1000, 2560, 640, True, 512),     # CTA pair, ragged M
+    (512, 1280, 1280, False, 64),     # 128x64 tiles, producer (bias + residual + statistics) and consumer
 ])
 def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
     """producer GEMM writes per-row (sum, sumsq) slabs; the consumer applies LayerNorm algebraically in its epilogue."""
@@ -118,7 +121,7 @@ def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
     bp = rnd(K, seed=33)
     res = rnd(M, K, seed=34) * 2 + 0.5            # non-zero mean rows
     stats = torch.full(((K + 63) // 64, M, 2), float("nan"), dtype=torch.float32, device="cuda")
-    h = ops.linear(a, wp, bp, residual=res, stats_out=stats)
+    h = ops.linear(a, wp, bp, residual=res, stats_out=stats, tile_n=64 if tile_n == 64 else 0)
     hf = h.float()
     # the statistics are those of the ROUNDED fp16 output rows
     s = stats.sum(dim=0)
@@ -177,7 +180,7 @@ def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [
     (2, 32, 32, 1280, 1280, 1), (2, 64, 64, 640, 640, 1), (1, 24, 24, 128, 320, 1), (2, 64, 64, 320, 320, 2),
 ])
-@pytest.mark.parametrize("tile_n", [512, 192, 384])
+@pytest.mark.parametrize("tile_n", [512, 192, 384, 64])
 def test_conv3x3_tile_variants(ops, B, H, W, Cin, Cout, stride, tile_n):
     x_nchw = rnd(B, Cin, H, W)
     w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)

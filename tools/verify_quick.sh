@@ -1,6 +1,5 @@
 #!/bin/bash
 set -u
-for v in 1 2 3; do
-  echo "variant $v: $(IH_ATTN_VARIANT=$v python -m pytest tests/test_kernels_gpu.py -q -k 'attention or attn' 2>&1 | tail -1)"
-done
-AB_CONFIGS='BASE=1 IH_ATTN_VARIANT=1 IH_ATTN_VARIANT=2 IH_ATTN_VARIANT=3' bash tools/ab_env.sh
+echo "kernels: $(IH_BN64_CONV=1 python -m pytest tests/test_kernels_gpu.py -q 2>&1 | tail -1)"
+IH_BN64_CONV=1 python -m pytest tests/test_unet_gpu.py -q -s -k "512 or tiny" 2>&1 | grep -E "^\[unet SDXL|passed|failed|FAILED|Error" | tail -6
+AB_CONFIGS='BASE=1 IH_BN64_CONV=1' bash tools/ab_env.sh
