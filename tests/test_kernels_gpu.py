@@ -113,6 +113,7 @@ def test_gemm_geglu(ops, M, C, tile_n):
     (2048, 5120, 1280, True, 0),      # norm3 -> GEGLU projection
     (1000, 2560, 640, True, 512),     # CTA pair, ragged M
     (512, 1280, 1280, False, 64),     # 128x64 tiles, producer (bias + residual + statistics) and consumer
+    (2048, 3840, 1280, False, 512),   # q|k|v consumer on the CTA-pair 256x256 tile
 ])
 def test_gemm_layernorm_fold(ops, M, N, K, geglu, tile_n):
     """producer GEMM writes per-row (sum, sumsq) slabs; the consumer applies LayerNorm algebraically in its epilogue."""
