@@ -20,6 +20,69 @@ def test_split_ip_adapter_checkpoint_matches_convert_bin_layout():
     assert set(got["composed_adapter"]) == {"fc1.weight"}                       # the frozen UNet keys are dropped
 
 
+def _flat_training_checkpoint():
+    g = torch.Generator("cpu").manual_seed(3)
+    r = lambda *shape: torch.randn(*shape, generator=g)   # noqa: E731
+    return {"image_proj_model.proj.weight": r(8, 4), "image_proj_model.proj.bias": r(8), "image_proj_model.norm.weight": r(4),
+            "adapter_modules.1.to_k_ip.weight": r(6, 5), "adapter_modules.1.to_v_ip.weight": r(6, 5),
+            "adapter_modules.3.to_k_ip.weight": r(6, 5), "composed_modules.fc1.weight": r(7, 3), "composed_modules.ln.bias": r(7),
+            "unet.conv_in.weight": r(2, 2, 3, 3)}
+
+
+def test_convert_bin_tool(tmp_path, capsys):
+    """convert_bin.convert_checkpoint_to_ip_adapter: the reference tool's contract (convert_bin.py:5-49) -- True + a 3-key
+    file, False (and no file) for a missing source or a checkpoint without the three prefixes."""
+    import convert_bin
+    flat = _flat_training_checkpoint()
+    src, dst = tmp_path / "pytorch_model.bin", tmp_path / "ip_adapter.bin"
+    torch.save(flat, src)
+    assert convert_bin.convert_checkpoint_to_ip_adapter(str(src), str(dst)) is True
+    got = torch.load(dst, map_location="cpu")
+    assert list(got) == ["image_proj", "ip_adapter", "composed_adapter"]           # convert_bin.py:34-38
+    assert list(got["ip_adapter"]) == ["1.to_k_ip.weight", "1.to_v_ip.weight", "3.to_k_ip.weight"]   # source order kept
+    for part, prefix in (("image_proj", "image_proj_model."), ("ip_adapter", "adapter_modules."),
+                         ("composed_adapter", "composed_modules.")):
+        for k, v in got[part].items():
+            assert torch.equal(v, flat[prefix + k])
+    assert sum(len(v) for v in got.values()) == len(flat) - 1                       # the frozen UNet key is dropped
+    assert convert_bin.convert_checkpoint_to_ip_adapter(str(tmp_path / "absent.bin"), str(tmp_path / "x.bin")) is False
+    torch.save({"unet.conv_in.weight": torch.ones(1)}, tmp_path / "other.bin")
+    assert convert_bin.convert_checkpoint_to_ip_adapter(str(tmp_path / "other.bin"), str(tmp_path / "y.bin")) is False
+    (tmp_path / "garbage.bin").write_bytes(b"not a checkpoint")
+    assert convert_bin.convert_checkpoint_to_ip_adapter(str(tmp_path / "garbage.bin"), str(tmp_path / "z.bin")) is False
+    assert not any((tmp_path / n).exists() for n in ("x.bin", "y.bin", "z.bin"))
+    # command line: a directory of checkpoint-* folders
+    os.makedirs(tmp_path / "run" / "checkpoint-100")
+    torch.save(flat, tmp_path / "run" / "checkpoint-100" / "pytorch_model.bin")
+    assert convert_bin._main([str(tmp_path / "run")]) == 0
+    assert (tmp_path / "run" / "checkpoint-100" / "ip_adapter.bin").exists()
+    capsys.readouterr()
+
+
+def test_convert_bin_tool_agrees_with_the_reference_tool(tmp_path, capsys):
+    """Where the reference tree is on disk (this container, not the GPU box): the reference's own converter and ours
+    write the same file for the same training checkpoint."""
+    import importlib.util
+    import pytest
+    ref_path = "/root/reference/convert_bin.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present")
+    import convert_bin
+    spec = importlib.util.spec_from_file_location("reference_convert_bin", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    src = tmp_path / "pytorch_model.bin"
+    torch.save(_flat_training_checkpoint(), src)
+    assert ref.convert_checkpoint_to_ip_adapter(str(src), str(tmp_path / "ref.bin")) is True
+    assert convert_bin.convert_checkpoint_to_ip_adapter(str(src), str(tmp_path / "own.bin")) is True
+    a, b = torch.load(tmp_path / "ref.bin", map_location="cpu"), torch.load(tmp_path / "own.bin", map_location="cpu")
+    assert list(a) == list(b)
+    for part in a:
+        assert list(a[part]) == list(b[part])
+        assert all(torch.equal(a[part][k], b[part][k]) for k in a[part])
+    capsys.readouterr()
+
+
 def test_infer_harmony_dims_from_shapes():
     from imagharmony_b200.config import HARMONY_DEFAULT as h
     from imagharmony_b200.weights import infer_harmony_dims, shapes_of
