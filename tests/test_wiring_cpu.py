@@ -159,6 +159,10 @@ def test_ip_adapter_xl_generate_call_surface(patched, tmp_path):
     from tutorial_train_sdxl_ori import ComposedAttention, HarmonyAttention   # demo.py:11 / ip_adapter.py:10 import paths
     from train import HarmonyAttention as HA2                                  # test.py:5 import path
     assert HA2 is HarmonyAttention and ComposedAttention is HarmonyAttention
+    from shared_models import ImageProjModel as IPM1                           # train.py:23 import path
+    from ip_adapter.shared_models import ImageProjModel as IPM2                # the package's identical copy
+    from ip_adapter.ip_adapter import ImageProjModel as IPM3                   # ip_adapter.py:26-48
+    assert IPM1 is IPM2 is IPM3
 
     from imagharmony_b200.config import TINY_VAE
     pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu", vae_cfg=TINY_VAE)
