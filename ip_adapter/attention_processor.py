@@ -189,7 +189,7 @@ class IPAttnProcessor2_0(torch.nn.Module):
         if want_map:
             k_ip = kv.view(B, Nk, 2 * C)[:, Nk - n_ip:, :C].reshape(B, n_ip, attn.heads, 64).permute(0, 2, 1, 3)
             qh = q.reshape(B, N, attn.heads, 64).permute(0, 2, 1, 3)
-            self.attn_map = qh @ k_ip.transpose(-2, -1).softmax(dim=-1)           # :443-444 (diagnostic only)
+            self.attn_map = qh @ k_ip.to(qh.dtype).transpose(-2, -1).softmax(dim=-1)   # :443-444 (diagnostic only)
         res2d = None if residual is None else residual.reshape(B * N, C)
         ops.prefetch_next(getattr(attn, "_next_w", None))
         out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=res2d, stats_out=stats_out)   # :453

@@ -376,3 +376,52 @@ def test_harmony_attention_groups_text_rows_per_image(patched):
     with torch.no_grad():
         wrong = ref(torch.cat([ta, ta]), img)
     assert (wrong[1] - want[1]).abs().max() > 1e-3
+
+
+def test_attention_map_hooks_match_oracle_and_reference_utils(patched):
+    """ip_adapter/utils.py diagnostics (utils.py:6-79): register_cross_attention_hook switches `attn_map` on in the active
+    IP processors and collects it per attn2 module; the maps equal the oracle processors' (attention_processor.py:443-444,
+    pinned against the reference class in oracle/check_against_reference.py); get_net_attn_map / attnmaps2images equal
+    the reference's own functions where the reference tree is on disk."""
+    import importlib.util
+    import os
+    import numpy as np
+    from imagharmony_b200.config import TINY
+    from ip_adapter import utils
+    native, ref = _build(TINY, 4)
+    utils.attn_maps.clear()
+    assert utils.register_cross_attention_hook(native) is native
+    active = {}
+    for name, proc in ref.attn_processors.items():
+        if getattr(proc, "skip", True) is False:
+            proc.keep_attn_map = True
+            active[name[:-len(".processor")]] = proc
+    assert active
+    sample, ehs, te, tid = _inputs(TINY, 1, 16)
+    with torch.no_grad():
+        ref(sample, 500.0, ehs, te, tid)
+        native(sample, torch.full((2,), 500.0), ehs, te, tid)
+    assert set(utils.attn_maps) == set(active)                       # skip=True layers produce no map
+    for name, proc in active.items():
+        got = utils.attn_maps[name]
+        assert got.shape == proc.attn_map.shape and got.shape[0] == 2 and got.shape[-1] == TINY.num_ip_tokens
+        # the native K/V cache is fp16 also on this fp32 stand-in path: fp16 rounding of k_ip, not fp32 round-off
+        assert torch.allclose(got.float(), proc.attn_map, rtol=2e-3, atol=2e-3), (got.float() - proc.attn_map).abs().max()
+        assert not hasattr(native.get_submodule(name).processor, "attn_map")      # moved out by the hook (utils.py:10-11)
+    net = utils.get_net_attn_map((128, 128), batch_size=2)
+    assert net.shape == (TINY.num_ip_tokens, 128, 128)
+    assert torch.allclose(net.sum(dim=0), torch.ones(128, 128), atol=1e-5)         # softmax over the tokens, layer mean
+    images = utils.attnmaps2images(net)
+    assert len(images) == TINY.num_ip_tokens and images[0].size == (128, 128) and images[0].mode == "L"
+    ref_path = "/root/reference/ip_adapter/utils.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("reference_ip_adapter_utils", ref_path)
+        ru = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ru)
+        ru.attn_maps.update({k: v.clone() for k, v in utils.attn_maps.items()})
+        for neg in (False, True):
+            a, b = utils.get_net_attn_map((128, 128), 2, neg), ru.get_net_attn_map((128, 128), 2, neg)
+            assert torch.equal(a, b)
+        for x, y in zip(images, ru.attnmaps2images(net)):
+            assert (np.asarray(x) == np.asarray(y)).all()
+    utils.attn_maps.clear()
