@@ -34,6 +34,8 @@ def register_cross_attention_hook(unet):
             module.register_forward_hook(hook_fn(name))
             if hasattr(getattr(module, "processor", None), "keep_attn_map"):
                 module.processor.keep_attn_map = True
+    if hasattr(unet, "graph_epoch"):
+        unet.graph_epoch += 1      # step graphs captured without the maps are stale (DenoiseEngine re-captures)
     return unet
 
 

@@ -390,7 +390,9 @@ def test_attention_map_hooks_match_oracle_and_reference_utils(patched):
     from ip_adapter import utils
     native, ref = _build(TINY, 4)
     utils.attn_maps.clear()
+    epoch = native.graph_epoch
     assert utils.register_cross_attention_hook(native) is native
+    assert native.graph_epoch == epoch + 1                            # graphs captured without the maps are stale
     active = {}
     for name, proc in ref.attn_processors.items():
         if getattr(proc, "skip", True) is False:
