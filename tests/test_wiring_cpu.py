@@ -427,3 +427,40 @@ def test_attention_map_hooks_match_oracle_and_reference_utils(patched):
         for x, y in zip(images, ru.attnmaps2images(net)):
             assert (np.asarray(x) == np.asarray(y)).all()
     utils.attn_maps.clear()
+
+
+def test_resampler_module_helpers(patched):
+    """ip_adapter/resampler.py module-level helpers with the reference's names (resampler.py:13-31, 150-158): FeedForward
+    keeps the reference's Sequential indices and computes LN -> Linear -> GELU -> Linear; reshape_tensor / masked_mean equal
+    the reference's functions where the reference tree is on disk."""
+    import importlib.util
+    import os
+    import torch.nn.functional as F
+    from ip_adapter import resampler as own
+    ff = own.FeedForward(32, mult=2).float()
+    assert list(ff.state_dict()) == ["0.weight", "0.bias", "1.weight", "3.weight"]          # resampler.py:15-20
+    g = torch.Generator("cpu").manual_seed(0)
+    with torch.no_grad():
+        for prm in ff.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * 0.2 + (1.0 if prm.ndim == 1 else 0.0))
+    x = torch.randn(2, 5, 32, generator=g)
+    want = F.linear(F.gelu(F.linear(F.layer_norm(x, (32,), ff[0].weight, ff[0].bias, ff[0].eps), ff[1].weight)), ff[3].weight)
+    with torch.no_grad():
+        got = ff(x)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (got - want).abs().max()
+    t = torch.randn(3, 7, 24, generator=g)
+    r = own.reshape_tensor(t, 4)
+    assert r.shape == (3, 4, 7, 6) and torch.equal(r[1, 2, 5], t[1, 5, 12:18])
+    mask = torch.rand(3, 7, generator=g) > 0.4
+    ref_path = "/root/reference/ip_adapter/resampler.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("reference_resampler", ref_path)
+        rr = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rr)
+        assert torch.equal(r, rr.reshape_tensor(t, 4))
+        assert torch.equal(own.masked_mean(t, dim=1), rr.masked_mean(t, dim=1))
+        assert torch.allclose(own.masked_mean(t, dim=1, mask=mask), rr.masked_mean(t, dim=1, mask=mask))
+        ref_ff = rr.FeedForward(32, mult=2)
+        ref_ff.load_state_dict(ff.state_dict())                                              # same keys, same layout
+        with torch.no_grad():
+            assert torch.allclose(got, ref_ff(x), rtol=1e-5, atol=1e-5)
