@@ -199,3 +199,7 @@ class IPAttnProcessor2_0(torch.nn.Module):
 # names the reference exports for torch < 2 / ControlNet are intentionally absent (out of scope)
 AttnProcessor = AttnProcessor2_0
 IPAttnProcessor = IPAttnProcessor2_0
+
+# `from ip_adapter.attention_processor import Cross_Attention` (train.py:32): HarmonyAttention's attention block
+# (attention_processor.py:12-56) lives with the adapter modules
+from imagharmony_b200.adapter import Cross_Attention  # noqa: E402,F401

@@ -163,6 +163,10 @@ def test_ip_adapter_xl_generate_call_surface(patched, tmp_path):
     from ip_adapter.shared_models import ImageProjModel as IPM2                # the package's identical copy
     from ip_adapter.ip_adapter import ImageProjModel as IPM3                   # ip_adapter.py:26-48
     assert IPM1 is IPM2 is IPM3
+    from ip_adapter.attention_processor import Cross_Attention as CA1           # train.py:32 import path
+    from imagharmony_b200.adapter import Cross_Attention as CA2
+    assert CA1 is CA2 and isinstance(HarmonyAttention(image_hidden_size=8, text_context_dim=8, inter_dim=16, cross_heads=2,
+                                                      reshape_blocks=2, cross_value_dim=4).fusion_text_image, CA1)
 
     from imagharmony_b200.config import TINY_VAE
     pipe = StableDiffusionXLCustomPipeline.from_random(TINY, seed=0, device="cpu", vae_cfg=TINY_VAE)
